@@ -1,0 +1,413 @@
+#!/usr/bin/env python
+"""bench.py -- points/sec (fwd+bwd) of the RandLA-Net hot path on N x B200 (BASELINE.json metric).
+
+    python bench.py --gpus 1 --steps 20 --warmup 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference --steps 5 --warmup 2       # the reference's CPU path (oracle port)
+
+One "step" = one pass of the hot path over one synthetic batch: forward + CrossEntropyLoss +
+backward (+ one flat NCCL gradient all-reduce when N > 1) + Adam update, on BASELINE.json configs[1]:
+full RandLA-Net (4 down / 4 up), K=16, 16 tiles x 12 800 points per GPU (weak scaling).
+
+Prints ONE JSON line (rank 0).  `value` is timed with inputs resident in HBM; `e2e` goes through the
+public `Model.training_step` with pinned HOST batches (H2D copies and the loss read-back inside the
+timed region); `roofline` is the dominant library kernel timed live with CUDA events in a separate
+profiling pass; `cpu_baseline` is the CPU oracle (the reference's PyTorch path restated) on a bounded
+sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "points/sec (fwd+bwd) RandLA-Net 12800-pt tiles"
+UNIT = "points/s"
+NUM_FEATURES, NUM_CLASSES, K_NEIGHBORS, DECIMATION = 9, 6, 16, 4
+LR = 0.003933  # configs/model/default.yaml:21-24
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--tiles", type=int, default=16, help="tiles per GPU per step (BASELINE configs[1]: 16)")
+    ap.add_argument("--points", type=int, default=12800, help="points per tile")
+    ap.add_argument("--cpu-tiles", type=int, default=4, help="tiles per step of the bounded CPU sample")
+    ap.add_argument("--cpu-steps", type=int, default=5)
+    ap.add_argument("--profile-steps", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--kernel-report", default=None, help="write the per-kernel table (JSON) here")
+    return ap.parse_args()
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------ synthetic data
+def host_batch(tiles: int, points: int, seed: int):
+    """Synthetic 50 m x 50 m Lidar-HD-like tiles as a pinned host Batch."""
+    from myria3d_b200 import Batch, Data
+    from oracle.randla_oracle import synthetic_tile  # data generator only (not a compute path)
+
+    datas = []
+    for t in range(tiles):
+        x, pos, y = synthetic_tile(points, seed + t, NUM_FEATURES, NUM_CLASSES)
+        datas.append(Data(x=x, pos=pos, y=y))
+    return Batch.from_data_list(datas)
+
+
+# ------------------------------------------------------------------------------ clocks sampler
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
+                 str(self.gpu_index)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        try:
+            self.proc.terminate()
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        try:
+            rows = [r.strip().split(", ") for r in open(self.path).read().strip().splitlines() if r.strip()]
+            sm = sorted(float(r[1]) for r in rows if len(r) >= 9)
+            if sm:
+                out["sm_mhz"] = sm[len(sm) // 2]
+                out["sm_max_mhz"] = max(float(r[2]) for r in rows if len(r) >= 9)
+                out["samples"] = len(sm)
+                names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+                for i, nm in enumerate(names):
+                    if any(r[5 + i].strip().lower() == "active" for r in rows if len(r) >= 9):
+                        out["reasons"].append(nm)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        return out
+
+
+# ------------------------------------------------------------------------------ roofline table
+def algorithmic_bytes(name: str, a):
+    """Compulsory HBM bytes of one library call (fp32 values, int32 neighbour ids)."""
+    if name == "b200_lfa_fwd":
+        n, c, kt = a
+        return n * (6 * c + 12 + 4 * kt)
+    if name == "b200_lfa_bwd":
+        n, c, kt = a
+        return n * (8 * c + 12 + 4 * kt)
+    if name == "b200_knn":
+        nx, ny, _clouds, _maxq, k, kt = a
+        return nx * 12 + ny * (12 + 4 * kt)
+    if name == "b200_edge_moments":
+        n, kt = a
+        return n * (12 + 4 * kt)
+    if name == "b200_linear_fwd":
+        _ld1, c1, _ld2, c2, n, cout = a
+        return 4 * n * (c1 + c2 + cout)
+    if name == "b200_linear_bwd_input":
+        _l1, c1, _l2, c2, n, cout = a
+        return 4 * n * (c1 + c2 + cout)
+    if name == "b200_linear_bwd_weight":
+        _l1, c1, _l2, c2, n, cout = a
+        return 4 * n * (c1 + c2 + cout)
+    if name == "b200_affine_act_fwd":
+        n, c = a
+        return 4 * n * c * 2
+    if name == "b200_affine_act_bwd_reduce":
+        n, c = a
+        return 4 * n * c * 3
+    if name == "b200_affine_act_bwd_apply":
+        n, c = a
+        return 4 * n * c * 4
+    if name in ("b200_gather_rows", "b200_scatter_rows_add"):
+        n, c = a
+        return n * (8 * c + 8)
+    if name == "b200_knn_interp_fwd":
+        ny, c, k, kt, _ld = a
+        return ny * (8 * c + 8 * kt)
+    if name == "b200_knn_interp_bwd":
+        _ld, ny, c, k, kt = a
+        return ny * (8 * c + 8 * kt)
+    return 0
+
+
+def kernel_table(records):
+    groups = {}
+    for name, ints, ms in records:
+        g = groups.setdefault((name, ints), {"name": name, "args": list(ints), "launches": 0, "ms": 0.0})
+        g["launches"] += 1
+        g["ms"] += ms
+    rows = sorted(groups.values(), key=lambda g: -g["ms"])
+    for g in rows:
+        g["ms_per_launch"] = g["ms"] / g["launches"]
+        g["alg_bytes"] = algorithmic_bytes(g["name"], tuple(g["args"]))
+        g["gbs"] = g["alg_bytes"] / (g["ms_per_launch"] * 1e-3) / 1e9 if g["ms_per_launch"] > 0 else 0.0
+    return rows
+
+
+# ------------------------------------------------------------------------------ CPU reference arm
+def cpu_reference(tiles: int, points: int, steps: int, warmup: int):
+    """The reference's CPU PyTorch path (oracle port): train-mode fwd + CE + bwd + Adam, kd-tree kNN."""
+    from oracle import randla_oracle as O
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(12345)
+    net = O.OracleRandLANet(NUM_FEATURES, NUM_CLASSES, decimation=DECIMATION, num_neighbors=K_NEIGHBORS,
+                            return_logits=True)
+    net.train()
+    opt = torch.optim.Adam(net.parameters(), lr=LR)
+    x, pos, y, batch, ptr = O.synthetic_batch([points] * tiles, seed=12345, num_features=NUM_FEATURES,
+                                              num_classes=NUM_CLASSES)
+
+    def step():
+        opt.zero_grad()
+        logits = net(x, pos, batch, ptr)
+        loss = F.cross_entropy(logits, y, ignore_index=65)
+        loss.backward()
+        opt.step()
+        return float(loss)
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return {"value": tiles * points / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{tiles} tiles x {points} pts per step, {warmup} warm-up + {steps} timed steps, "
+                      f"oracle/randla_oracle.py (pure torch CPU + scipy cKDTree, 1 kNN worker)",
+            "ms_per_step": dt * 1e3}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    res = cpu_reference(args.cpu_tiles, args.points, args.steps, max(args.warmup, 1))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    return {
+        "workload": f"RandLA-Net full (4 down/4 up), K={K_NEIGHBORS}, {args.points} pts/tile, batch={args.tiles}/GPU "
+                    f"(BASELINE configs[1]{'/[2]' if world > 1 else ''})",
+        "step": "fwd + CrossEntropyLoss + bwd + flat NCCL grad all-reduce (N>1) + Adam",
+        "num_features": NUM_FEATURES, "num_classes": NUM_CLASSES, "global_batch_tiles": args.tiles * world,
+        "points_per_step": args.tiles * args.points * world,
+        "parallelism": f"dp{world}", "l2": "256 MiB buffer rewritten between timed steps (outside the event pairs); "
+                                           "4 rotating input batches",
+    }
+
+
+# ------------------------------------------------------------------------------ B200 arm
+def run_b200(args):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from myria3d_b200 import Model, _lib
+    from myria3d_b200.build import build_library
+    from myria3d_b200.parallel import FlatGradAllReducer, broadcast_module_state
+
+    if rank == 0:
+        build_library()
+    if world > 1:
+        dist.barrier()
+    lib = _lib.load()
+    _lib.check(lib.b200_check_device(), "b200_check_device")
+
+    torch.manual_seed(12345)
+    model = Model(neural_net_class_name="B200RandLANet",
+                  neural_net_hparams=dict(num_features=NUM_FEATURES, num_classes=NUM_CLASSES, num_neighbors=K_NEIGHBORS,
+                                          decimation=DECIMATION, return_logits=True),
+                  criterion=torch.nn.CrossEntropyLoss(ignore_index=65), lr=LR).to(dev)
+    model.train()
+    broadcast_module_state(model)
+    reducer = FlatGradAllReducer(model)
+    opt = torch.optim.Adam(model.parameters(), lr=LR)
+
+    n_rot = 4
+    host = [host_batch(args.tiles, args.points, 12345 + 1000 * rank + 100 * r).pin_memory() for r in range(n_rot)]
+    resident = [b.to(dev) for b in host]
+    h2d_bytes = sum(t.numel() * t.element_size() for t in (host[0].x, host[0].pos, host[0].y, host[0].batch, host[0].ptr))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    points_per_step = args.tiles * args.points
+
+    def train_step(batch):
+        reducer.zero_grad()
+        out = model.training_step(batch, 0)
+        out["loss"].backward()
+        reducer.all_reduce()
+        opt.step()
+        return out["loss"]
+
+    def timed(kind: str, steps: int):
+        evs = []
+        for s in range(steps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            if kind == "resident":
+                train_step(resident[s % n_rot])
+            else:
+                b = host[s % n_rot].to(dev, non_blocking=True)
+                loss = train_step(b)
+                loss.item()  # device -> host read of the step's result
+            e1.record()
+            evs.append((e0, e1))
+        torch.cuda.synchronize()
+        return sum(a.elapsed_time(b) for a, b in evs)  # ms
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v: float) -> float:
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- warm-up, then the resident-input measurement
+    for s in range(max(args.warmup, 3)):
+        train_step(resident[s % n_rot])
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.launch_count()
+    barrier()
+    total_ms = timed("resident", args.steps)
+    barrier()
+    launches = (_lib.launch_count() - launches0) // max(args.steps, 1)
+    total_ms = max_over_ranks(total_ms)
+    # ---- end-to-end through Model.training_step with host batches
+    for s in range(2):
+        train_step(host[s % n_rot].to(dev, non_blocking=True)).item()
+    barrier()
+    e2e_ms = timed("e2e", args.steps)
+    barrier()
+    e2e_ms = max_over_ranks(e2e_ms)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- per-kernel pass (CUDA events around every library call) for the roofline object
+    table = []
+    if rank == 0 and args.profile_steps > 0:
+        prof = _lib.KernelProfiler()
+        _lib.PROFILER = prof
+        for s in range(args.profile_steps):
+            train_step(resident[s % n_rot])
+        _lib.PROFILER = None
+        recs = prof.summary()
+        table = kernel_table([(n, i, ms / 1.0) for n, i, ms in recs])
+        for g in table:
+            g["ms"] /= args.profile_steps
+            g["launches"] //= args.profile_steps
+    if world > 1:
+        dist.barrier()
+
+    if rank == 0:
+        ms_per_step = total_ms / args.steps
+        value = points_per_step * world / (ms_per_step * 1e-3)
+        e2e_val = points_per_step * world / (e2e_ms / args.steps * 1e-3)
+        peak, peak_src = peaks()
+        roof = None
+        if table:
+            top = table[0]
+            lib_ms = sum(g["ms"] for g in table)
+            roof = {"bound": "hbm", "kernel": top["name"], "kernel_args": top["args"],
+                    "achieved": top["gbs"], "peak": peak, "unit": "GB/s", "frac": top["gbs"] / peak,
+                    "traffic": None, "peak_source": peak_src, "launch_ms": top["ms_per_launch"],
+                    "share_of_library_time": top["ms"] / lib_ms if lib_ms > 0 else None,
+                    "library_ms_per_step": lib_ms}
+            report = args.kernel_report
+            if report is None and os.path.isdir(os.path.join(ROOT, "gpurun_out")):
+                report = os.path.join(ROOT, "gpurun_out", "bench_kernels.json")
+            if report:
+                with open(report, "w") as f:
+                    json.dump({"ms_per_step": ms_per_step, "kernels": table}, f, indent=1)
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            res = cpu_reference(args.cpu_tiles, args.points, args.cpu_steps, 2)
+            cpu = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
+            "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": 4,
+                    "ms_per_step": e2e_ms / args.steps},
+            "roofline": roof, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

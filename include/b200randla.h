@@ -1,0 +1,186 @@
+/*
+ * b200randla.h -- C ABI of libb200randla.so: the B200 (sm_100a) RandLA-Net hot path
+ * of IGNF/myria3d, as hand-written CUDA kernels behind plain pointers and sizes.
+ *
+ * Conventions:
+ *   - every pointer is a DEVICE pointer unless named host_*; the caller owns every
+ *     buffer (outputs and workspaces are pre-allocated by the caller);
+ *   - no allocation, no synchronisation, no global state inside: every entry point
+ *     only enqueues kernels on `stream` (a cudaStream_t passed as void*), so calls
+ *     are re-entrant, graph-capturable and safe from the autograd engine thread;
+ *   - floating tensors are fp32 row-major; neighbour tables are int32 [rows, kt]
+ *     with kt the TABLE WIDTH (16 or 32 for the LFA kernels), -1 padded: clouds
+ *     smaller than k give min(k, n_cloud) neighbours (torch_cluster semantics);
+ *     `ptr` arrays are int64 [B+1] exactly as PyG's Batch.ptr;
+ *   - return value 0 = ok; non-zero = error (B200_E_*), message via b200_last_error().
+ *     Asynchronous CUDA errors surface at the caller's next synchronisation.
+ *
+ * Each entry point cites the reference call it replaces (paths relative to the
+ * myria3d repository root).
+ */
+#ifndef B200RANDLA_H_
+#define B200RANDLA_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_ABI_VERSION 1
+
+#define B200_OK 0
+#define B200_E_INVALID 1     /* bad argument (null pointer, unsupported size/alignment) */
+#define B200_E_UNSUPPORTED 2 /* valid request this build has no kernel for */
+#define B200_E_CUDA 3        /* a CUDA runtime call failed at enqueue time */
+
+int b200_abi_version(void);
+/* Thread-local message of the last failing call on this thread ("" if none). */
+const char* b200_last_error(void);
+/* Number of kernels this library has enqueued since load (all threads). */
+int64_t b200_launch_count(void);
+/* cudaGetDeviceProperties-based sanity check: 0 iff the current device is sm_100. */
+int b200_check_device(void);
+
+/* ---------------------------------------------------------------- kNN ------------------
+ * Replaces torch_cluster knn()/knn_graph() as called by
+ *   knn_graph(pos, k, batch=batch, loop=True)   myria3d/models/modules/pyg_randla_net.py:180
+ *   knn_interpolate(..., k=1)                   myria3d/models/modules/pyg_randla_net.py:250
+ *   knn_interpolate(..., k=interpolation_k)     myria3d/models/model.py:90
+ * For every query y (cloud b = the segment [ptr_y[b], ptr_y[b+1])) the k nearest x of
+ * the SAME cloud, ascending by fp32 squared distance ((dx*dx+dy*dy)+dz*dz, no FMA),
+ * ties to the lower x index; self is included when x == y.
+ *   nbr   int32 [ny, kt]  global x indices, -1 padded beyond min(k, n_cloud) and beyond k
+ *   dist2 fp32  [ny, kt]  matching squared distances (+inf padded); may be NULL
+ * max_queries_per_cloud bounds the launch grid (host knows ptr).
+ */
+int b200_knn(const float* pos_x, const int64_t* ptr_x, int64_t nx,
+             const float* pos_y, const int64_t* ptr_y, int64_t ny,
+             int32_t num_clouds, int64_t max_queries_per_cloud,
+             int32_t k, int32_t kt, int32_t* nbr, float* dist2, void* stream);
+
+/* ------------------------------------------------------- LocSE / attentive pooling -----
+ * Together these replace LocalFeatureAggregation.propagate()+message()
+ * (myria3d/models/modules/pyg_randla_net.py:121-152): gather, relative position
+ * encoding, encoder SharedMLP, concat, attention Linear, neighbourhood softmax
+ * (torch_geometric.utils.softmax), weighting and the aggr="add" scatter.
+ *
+ * b200_edge_moments: first and second moments of q = (p_i, p_j, |p_j-p_i|) in R^7 over
+ * all valid edges, in fp64: out[0]=edge count, out[1..7]=sum q, out[8..56]=sum q q^T
+ * (row-major 7x7).  `out` (57 doubles) must be zeroed by the caller.  With them the
+ * train-mode BatchNorm of mlp_encoder (statistics over all E edges, pyg_randla_net.py:117,144)
+ * folds into an affine map, so the fused kernels below are single-pass in training too.
+ */
+int b200_edge_moments(const float* pos, const int32_t* nbr, int64_t n, int32_t kt,
+                      double* out, void* stream);
+
+/* Fused forward.  c = channels of the LFA (x has h = c/2 features).
+ *   x       fp32 [n, h]        pos fp32 [n, 3]      nbr int32 [n, kt]
+ *   enc_w   fp32 [h, 7]        encoder weight acting on q=(p_i,p_j,dist), BatchNorm folded in
+ *   enc_b   fp32 [h]           folded bias
+ *   att_wt  fp32 [c, c]        TRANSPOSE of mlp_attention.lins.0.weight (att_wt[m][n] = W[n][m])
+ *   out     fp32 [n, c]        sum_j softmax_j(W f_ij) * f_ij,  f_ij = [x_j ; lrelu(enc_w q_ij + enc_b)]
+ */
+int b200_lfa_fwd(const float* x, const float* pos, const int32_t* nbr,
+                 const float* enc_w, const float* enc_b, const float* att_wt,
+                 float* out, int64_t n, int32_t c, int32_t kt, void* stream);
+
+/* Fused backward (recomputes the forward per tile).  grad_x / grad_enc_w / grad_enc_b /
+ * grad_att_w are ACCUMULATED into (atomics): the caller zero-fills them.
+ *   att_w   fp32 [c, c]  mlp_attention.lins.0.weight as stored ([out, in])
+ *   grad_att_w fp32 [c, c] in the same [out, in] layout
+ */
+int b200_lfa_bwd(const float* x, const float* pos, const int32_t* nbr,
+                 const float* enc_w, const float* enc_b, const float* att_wt, const float* att_w,
+                 const float* grad_out,
+                 float* grad_x, float* grad_enc_w, float* grad_enc_b, float* grad_att_w,
+                 int64_t n, int32_t c, int32_t kt, void* stream);
+
+/* ------------------------------------------------------- index / scatter kernels -------
+ * b200_gather_rows: out[i, :] = src[idx[i], :]          (decimate, pyg_randla_net.py:237)
+ * b200_scatter_rows_add: dst[idx[i], :] += src[i, :]    (its backward; dst pre-zeroed)
+ * idx is int64 (what torch.randperm yields at pyg_randla_net.py:221).
+ */
+int b200_gather_rows(const float* src, const int64_t* idx, float* out,
+                     int64_t n_out, int32_t c, void* stream);
+int b200_scatter_rows_add(const float* src, const int64_t* idx, float* dst,
+                          int64_t n_src, int32_t c, void* stream);
+
+/* Inverse-squared-distance kNN interpolation = torch_geometric knn_interpolate's tail
+ * (pyg_randla_net.py:250 with k=1; model.py:90-98 with k=10):
+ *   w_e = 1 / max(d2_e, 1e-16);  y_i = (sum_e x[nbr_e] * w_e) / (sum_e w_e)
+ * with the reference's rounding sequence (products, sequential sums in ascending-distance
+ * order, one IEEE division) so that k=1 reproduces (x*w)/w bit for bit.
+ *   nbr int32 [ny, kt], dist2 fp32 [ny, kt] from b200_knn; -1 entries are skipped.
+ *   out fp32 [ny, ld_out] written at columns [0, c)  (ld_out >= c lets the caller
+ *   interpolate straight into the left part of a concat buffer).
+ * Backward: grad_x[nbr_e, :] += grad_y[i, :] * w_e / sum_e w_e   (grad_x pre-zeroed).
+ */
+int b200_knn_interp_fwd(const float* x, const int32_t* nbr, const float* dist2,
+                        float* out, int64_t ny, int32_t c, int32_t k, int32_t kt,
+                        int64_t ld_out, void* stream);
+int b200_knn_interp_bwd(const float* grad_y, int64_t ld_grad, const int32_t* nbr, const float* dist2,
+                        float* grad_x, int64_t ny, int32_t c, int32_t k, int32_t kt, void* stream);
+
+/* ------------------------------------------------------- per-point shared MLP ----------
+ * Replace SharedMLP = PyG MLP(Linear -> BatchNorm1d(momentum .01, eps 1e-6) -> LeakyReLU(.2))
+ * (pyg_randla_net.py:97-109) on [n, c] rows, torch.nn.Linear for fc0 / fc_classif
+ * (pyg_randla_net.py:42,53) and the block tail lrelu(mlp2(x) + shortcut(x)) (:186-187).
+ *
+ * b200_linear_fwd:  y[n, cout] = [a1 | a2] W^T + bias
+ *   a1 fp32 [n, c1] (row stride ld1), a2 fp32 [n, c2] (row stride ld2) or NULL with c2 = 0:
+ *   the K dimension is the concatenation (FPModule's torch.cat, pyg_randla_net.py:251).
+ *   w fp32 [cout, c1+c2] row-major, bias fp32 [cout] or NULL.
+ *   If colstats != NULL (fp64 [2*cout], pre-zeroed) the epilogue also accumulates
+ *   sum_i y[i,ch] and sum_i y[i,ch]^2 for the BatchNorm that follows.
+ */
+int b200_linear_fwd(const float* a1, int64_t ld1, int32_t c1, const float* a2, int64_t ld2, int32_t c2,
+                    const float* w, const float* bias, float* y, int64_t n, int32_t cout,
+                    double* colstats, void* stream);
+/* grad_a[n, c1+c2 split as ga1|ga2] = grad_y W ; either output may be NULL (skipped). */
+int b200_linear_bwd_input(const float* grad_y, const float* w, float* ga1, int64_t ldg1, int32_t c1,
+                          float* ga2, int64_t ldg2, int32_t c2, int64_t n, int32_t cout, void* stream);
+/* grad_w[cout, c1+c2] += grad_y^T [a1|a2];  grad_bias[cout] += column sums of grad_y
+ * (both accumulated with atomics: caller zero-fills; grad_bias may be NULL). */
+int b200_linear_bwd_weight(const float* grad_y, const float* a1, int64_t ld1, int32_t c1,
+                           const float* a2, int64_t ld2, int32_t c2,
+                           float* grad_w, float* grad_bias, int64_t n, int32_t cout, void* stream);
+
+/* BatchNorm statistics -> per-channel affine.  colstats fp64 [2*c] = (sum, sum of squares)
+ * over `count` rows.  Writes scale = gamma*invstd, shift = beta - mean*scale, and
+ * mean / invstd (saved for backward).  If running_mean != NULL updates the running
+ * statistics in place: r = (1-momentum) r + momentum * stat (unbiased variance).
+ * With colstats == NULL (eval mode) uses the running statistics instead. */
+int b200_bn_finalize(const double* colstats, int64_t count, const float* gamma, const float* beta,
+                     float* running_mean, float* running_var, float momentum, float eps,
+                     float* scale, float* shift, float* mean, float* invstd, int32_t c, void* stream);
+
+/* out = act(y1*scale1 + shift1 [+ y2*scale2 + shift2]) ; act = LeakyReLU(slope) (slope = 1: identity). */
+int b200_affine_act_fwd(const float* y1, const float* scale1, const float* shift1,
+                        const float* y2, const float* scale2, const float* shift2,
+                        float slope, float* out, int64_t n, int32_t c, void* stream);
+
+/* Backward, pass 1: g = grad_out * act'(out); accumulates (fp64, pre-zeroed)
+ *   red1[0:c] = sum g,  red1[c:2c] = sum g * (y1 - mean1) * invstd1   (and red2 likewise for y2). */
+int b200_affine_act_bwd_reduce(const float* grad_out, const float* out, float slope,
+                               const float* y1, const float* mean1, const float* invstd1, double* red1,
+                               const float* y2, const float* mean2, const float* invstd2, double* red2,
+                               int64_t n, int32_t c, void* stream);
+/* Backward, pass 2 (train-mode BatchNorm): with xhat = (y - mean) * invstd,
+ *   grad_y = gamma*invstd * (g - red[0:c]/n - xhat * red[c:2c]/n),
+ *   grad_gamma = red[c:2c], grad_beta = red[0:c]  (written, not accumulated).
+ * Eval mode / plain affine (red == NULL): grad_y = g * scale.
+ * grad_y2 (second branch) is produced when y2 != NULL. */
+int b200_affine_act_bwd_apply(const float* grad_out, const float* out, float slope,
+                              const float* y1, const float* gamma1, const float* mean1, const float* invstd1,
+                              const double* red1, const float* scale1, float* grad_y1,
+                              float* grad_gamma1, float* grad_beta1,
+                              const float* y2, const float* gamma2, const float* mean2, const float* invstd2,
+                              const double* red2, const float* scale2, float* grad_y2,
+                              float* grad_gamma2, float* grad_beta2,
+                              int64_t n, int32_t c, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200RANDLA_H_ */

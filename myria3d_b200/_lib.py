@@ -1,0 +1,103 @@
+"""ctypes binding of ``libb200randla.so`` (C ABI declared in ``include/b200randla.h``).
+
+There is NO CPU fallback: if the shared object is missing or a call fails the error is raised.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_void_p
+from pathlib import Path
+
+import torch  # noqa: F401  (loads the CUDA runtime the library links against)
+
+LIB_PATH = Path(__file__).resolve().parent / "libb200randla.so"
+
+_P = c_void_p
+_SIGNATURES = {
+    "b200_abi_version": (c_int, []),
+    "b200_last_error": (c_char_p, []),
+    "b200_launch_count": (c_int64, []),
+    "b200_check_device": (c_int, []),
+    "b200_knn": (c_int, [_P, _P, c_int64, _P, _P, c_int64, c_int32, c_int64, c_int32, c_int32, _P, _P, _P]),
+    "b200_edge_moments": (c_int, [_P, _P, c_int64, c_int32, _P, _P]),
+    "b200_lfa_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int64, c_int32, c_int32, _P]),
+    "b200_lfa_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int32, c_int32, _P]),
+    "b200_gather_rows": (c_int, [_P, _P, _P, c_int64, c_int32, _P]),
+    "b200_scatter_rows_add": (c_int, [_P, _P, _P, c_int64, c_int32, _P]),
+    "b200_knn_interp_fwd": (c_int, [_P, _P, _P, _P, c_int64, c_int32, c_int32, c_int32, c_int64, _P]),
+    "b200_knn_interp_bwd": (c_int, [_P, c_int64, _P, _P, _P, c_int64, c_int32, c_int32, c_int32, _P]),
+    "b200_linear_fwd": (c_int, [_P, c_int64, c_int32, _P, c_int64, c_int32, _P, _P, _P, c_int64, c_int32, _P, _P]),
+    "b200_linear_bwd_input": (c_int, [_P, _P, _P, c_int64, c_int32, _P, c_int64, c_int32, c_int64, c_int32, _P]),
+    "b200_linear_bwd_weight": (c_int, [_P, _P, c_int64, c_int32, _P, c_int64, c_int32, _P, _P, c_int64, c_int32, _P]),
+    "b200_bn_finalize": (c_int, [_P, c_int64, _P, _P, _P, _P, c_float, c_float, _P, _P, _P, _P, c_int32, _P]),
+    "b200_affine_act_fwd": (c_int, [_P, _P, _P, _P, _P, _P, c_float, _P, c_int64, c_int32, _P]),
+    "b200_affine_act_bwd_reduce": (c_int, [_P, _P, c_float, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int32, _P]),
+    "b200_affine_act_bwd_apply": (
+        c_int,
+        [_P, _P, c_float, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int32, _P],
+    ),
+}
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+ABI_VERSION = 1
+
+_lib = None
+
+# Set to a KernelProfiler to time every library call with CUDA events (bench.py's roofline pass).
+PROFILER = None
+
+
+class KernelProfiler:
+    """Collects (entry point, integer arguments, start event, end event) per library call."""
+
+    def __init__(self):
+        self.records = []
+
+    def add(self, name, args, start, end):
+        ints = tuple(a for a in args if isinstance(a, int))
+        self.records.append((name, ints, start, end))
+
+    def summary(self):
+        """Synchronise and return ``[(name, ints, milliseconds), ...]``."""
+        import torch
+
+        torch.cuda.synchronize()
+        return [(n, ints, s.elapsed_time(e)) for n, ints, s, e in self.records]
+
+
+
+class B200Error(RuntimeError):
+    """A libb200randla entry point returned a non-zero status."""
+
+
+def load() -> ctypes.CDLL:
+    """Load (once) and type the shared library.  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise B200Error(
+            f"{LIB_PATH} is missing: build it with `python -m myria3d_b200.build` "
+            "(there is no CPU or PyTorch fallback for the B200 hot path)"
+        )
+    lib = ctypes.CDLL(os.fspath(LIB_PATH))
+    for name, (restype, argtypes) in _SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = restype
+        fn.argtypes = argtypes
+    if lib.b200_abi_version() != ABI_VERSION:
+        raise B200Error(f"ABI mismatch: library {lib.b200_abi_version()} != binding {ABI_VERSION}")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().b200_last_error().decode("utf-8", "replace")
+        if rc == 1:
+            raise ValueError(f"{what}: {msg}")
+        raise B200Error(f"{what}: {msg} (code {rc})")
+
+
+def launch_count() -> int:
+    return int(load().b200_launch_count())

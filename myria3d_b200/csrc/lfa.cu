@@ -1,0 +1,687 @@
+// Fused Local Spatial Encoding + attentive pooling (forward, backward) and the edge-moment
+// pre-pass, for sm_100a.
+//
+// Replaces LocalFeatureAggregation.propagate()/message() of
+// myria3d/models/modules/pyg_randla_net.py:121-152 -- in the reference ~20 library kernels over
+// ~18 materialised [E, .] tensors -- by ONE kernel per direction that keeps
+// every per-edge quantity on chip:
+//
+//   tile   = TC centres x KT neighbour slots, processed by TC * (C/CW) threads; a persistent grid
+//            walks the tiles.
+//   build  : neighbour ids, (p_j, |p_j-p_i|) and p_i go to shared memory; F[edge][0:H) = x_j
+//            (vectorised gathers), F[edge][H:C) = lrelu(enc_w . (p_i, p_j, dist) + enc_b).  The
+//            10-d relative position vector of the reference is linear in those 7 numbers and the
+//            encoder BatchNorm is linear in it, so both are folded into enc_w/enc_b on the host
+//            (SURVEY.md App. D-7, D-8).
+//   GEMM1  : a[k][n] = sum_m F[k][m] W_att[n][m]; thread (centre g, column group q) owns all KT
+//            rows of its centre for CW columns -> the neighbourhood softmax and the weighted sum
+//            are thread-local register reductions (no atomics, no scatter).
+//   backward additionally: da = s*go*(f-o) to shared memory, GEMM2 dF = da.W + s*go (register
+//            accumulators initialised with the direct term), x-gradients by vector red.global,
+//            encoder-gradient partials in shared memory, GEMM3 dW += da^T F as 4x4 register blocks.
+//
+// TODO(round 2): the three contractions run on the fp32 FMA pipe here; the tcgen05/TMEM version
+// maps channels to TMEM lanes and edges to columns so that the same thread-local softmax applies.
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace b200 {
+
+// ------------------------------------------------------------------------------------------
+// edge moments: count, sum q, sum q q^T (fp64) with q = (p_i, p_j, |p_j - p_i|)
+// ------------------------------------------------------------------------------------------
+constexpr int MOM_THREADS = 128;
+constexpr int MOM_VALS = 1 + 7 + 28;  // count, sums, upper triangle
+
+__global__ void __launch_bounds__(MOM_THREADS)
+edge_moments_kernel(const float* __restrict__ pos, const int32_t* __restrict__ nbr, int64_t n, int kt,
+                    double* __restrict__ out) {
+  double acc[MOM_VALS];
+#pragma unroll
+  for (int i = 0; i < MOM_VALS; ++i) acc[i] = 0.0;
+
+  for (int64_t i = (int64_t)blockIdx.x * MOM_THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * MOM_THREADS) {
+    const float pix = pos[3 * i], piy = pos[3 * i + 1], piz = pos[3 * i + 2];
+    const int32_t* row = nbr + i * kt;
+    for (int k = 0; k < kt; ++k) {
+      const int j = row[k];
+      if (j < 0) break;  // valid neighbours are a prefix
+      const float pjx = pos[3 * (int64_t)j], pjy = pos[3 * (int64_t)j + 1], pjz = pos[3 * (int64_t)j + 2];
+      const float dx = pjx - pix, dy = pjy - piy, dz = pjz - piz;
+      const float dist = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+      const double q[7] = {pix, piy, piz, pjx, pjy, pjz, dist};
+      acc[0] += 1.0;
+      int t = 8;
+#pragma unroll
+      for (int a = 0; a < 7; ++a) {
+        acc[1 + a] += q[a];
+#pragma unroll
+        for (int b = a; b < 7; ++b) acc[t++] += q[a] * q[b];
+      }
+    }
+  }
+
+  __shared__ double red[MOM_THREADS / 32][MOM_VALS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < MOM_VALS; ++i) {
+    const double v = warp_sum(acc[i]);
+    if (lane == 0) red[warp][i] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < MOM_VALS) {
+    double v = 0.0;
+    for (int w = 0; w < MOM_THREADS / 32; ++w) v += red[w][threadIdx.x];
+    const int i = threadIdx.x;
+    if (i < 8) {
+      atomicAdd(out + i, v);
+    } else {
+      // unpack the upper-triangle slot into both symmetric positions of the 7x7 matrix
+      int t = 8, ra = 0, rb = 0;
+      for (int a = 0; a < 7; ++a)
+        for (int b = a; b < 7; ++b) {
+          if (t == i) {
+            ra = a;
+            rb = b;
+          }
+          ++t;
+        }
+      atomicAdd(out + 8 + ra * 7 + rb, v);
+      if (ra != rb) atomicAdd(out + 8 + rb * 7 + ra, v);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// tile configuration
+// ------------------------------------------------------------------------------------------
+template <int C_, int KT_, int CW_, int TC_>
+struct LfaCfg {
+  static constexpr int C = C_, KT = KT_, CW = CW_, TC = TC_;
+  static constexpr int H = C / 2;
+  static constexpr int TPC = C / CW;          // threads per centre
+  static constexpr int THREADS = TC * TPC;
+  static constexpr int EDGES = TC * KT;
+  static constexpr int CSTRIDE = KT * C + 4;  // floats per centre block (+4: spreads centres over banks)
+  static constexpr int TILE_FLOATS = TC * CSTRIDE;
+  static_assert(H % 4 == 0, "H must be a multiple of 4");
+  static_assert(H % CW == 0, "a thread's columns must not straddle the x | encoding boundary");
+  static_assert(THREADS % H == 0 || H % THREADS == 0, "encoder build mapping");
+  static_assert(THREADS % 32 == 0, "whole warps");
+};
+
+template <int CW>
+__device__ __forceinline__ void load_vec(float (&v)[CW], const float* __restrict__ p) {
+  if constexpr (CW == 8) {
+    const float4 a = *reinterpret_cast<const float4*>(p);
+    const float4 b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
+  } else if constexpr (CW == 4) {
+    const float4 a = *reinterpret_cast<const float4*>(p);
+    v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w;
+  } else {
+    static_assert(CW == 2, "CW in {2,4,8}");
+    const float2 a = *reinterpret_cast<const float2*>(p);
+    v[0] = a.x, v[1] = a.y;
+  }
+}
+template <int CW>
+__device__ __forceinline__ void ldg_vec(float (&v)[CW], const float* __restrict__ p) {
+  if constexpr (CW == 8) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(p + 4));
+    v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
+  } else if constexpr (CW == 4) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+    v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w;
+  } else {
+    const float2 a = __ldg(reinterpret_cast<const float2*>(p));
+    v[0] = a.x, v[1] = a.y;
+  }
+}
+template <int CW>
+__device__ __forceinline__ void store_vec(float* __restrict__ p, const float (&v)[CW]) {
+  if constexpr (CW == 8) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  } else if constexpr (CW == 4) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  } else {
+    *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]);
+  }
+}
+// vector reduction into global memory (red.global.add.v4.f32 / v2.f32 on sm_90+)
+template <int CW>
+__device__ __forceinline__ void red_vec(float* __restrict__ p, const float (&v)[CW]) {
+  if constexpr (CW == 8) {
+    atomicAdd(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3]));
+    atomicAdd(reinterpret_cast<float4*>(p + 4), make_float4(v[4], v[5], v[6], v[7]));
+  } else if constexpr (CW == 4) {
+    atomicAdd(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3]));
+  } else {
+    atomicAdd(reinterpret_cast<float2*>(p), make_float2(v[0], v[1]));
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// build one tile: NB (neighbour ids), Q (p_j, dist), P (p_i), F (features)
+// ------------------------------------------------------------------------------------------
+template <class Cfg>
+__device__ __forceinline__ void lfa_build_tile(int64_t tile_base, int64_t n, const float* __restrict__ x,
+                                               const float* __restrict__ pos, const int32_t* __restrict__ nbr,
+                                               const float* __restrict__ enc_w, const float* __restrict__ enc_b,
+                                               float* __restrict__ F, float4* __restrict__ Q,
+                                               float4* __restrict__ P, int* __restrict__ NB) {
+  constexpr int C = Cfg::C, KT = Cfg::KT, H = Cfg::H, THREADS = Cfg::THREADS, EDGES = Cfg::EDGES;
+  constexpr int CSTRIDE = Cfg::CSTRIDE;
+  const int tid = threadIdx.x;
+
+  for (int e = tid; e < EDGES; e += THREADS) {
+    const int g = e / KT, kk = e % KT;
+    const int64_t i = tile_base + g;
+    int j = -1;
+    float4 qv = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 pv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < n) {
+      j = __ldg(nbr + i * KT + kk);
+      pv = make_float4(__ldg(pos + 3 * i), __ldg(pos + 3 * i + 1), __ldg(pos + 3 * i + 2), 0.f);
+      if (j >= 0) {
+        const float pjx = __ldg(pos + 3 * (int64_t)j), pjy = __ldg(pos + 3 * (int64_t)j + 1),
+                    pjz = __ldg(pos + 3 * (int64_t)j + 2);
+        const float dx = pjx - pv.x, dy = pjy - pv.y, dz = pjz - pv.z;
+        const float dist = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+        qv = make_float4(pjx, pjy, pjz, dist);
+      }
+    }
+    NB[e] = j;
+    Q[e] = qv;
+    if (kk == 0) P[g] = pv;
+  }
+  __syncthreads();
+
+  // x_j gather into F[:, 0:H)
+  constexpr int H4 = H / 4;
+  const float4* x4 = reinterpret_cast<const float4*>(x);
+  for (int t = tid; t < EDGES * H4; t += THREADS) {
+    const int e = t / H4, m4 = t % H4;
+    const int j = NB[e];
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (j >= 0) v = __ldg(x4 + (int64_t)j * H4 + m4);
+    *reinterpret_cast<float4*>(F + (e / KT) * CSTRIDE + (e % KT) * C + m4 * 4) = v;
+  }
+
+  // encoder into F[:, H:C)
+  if constexpr (THREADS >= H) {
+    constexpr int EPI = THREADS / H;  // edges handled per iteration
+    const int m = tid % H, e0 = tid / H;
+    float w[7];
+#pragma unroll
+    for (int t = 0; t < 7; ++t) w[t] = __ldg(enc_w + m * 7 + t);
+    const float b = __ldg(enc_b + m);
+    for (int e = e0; e < EDGES; e += EPI) {
+      const int g = e / KT;
+      float v = 0.f;
+      if (NB[e] >= 0) {
+        const float4 p = P[g], q = Q[e];
+        float z = b;
+        z = fmaf(w[0], p.x, z), z = fmaf(w[1], p.y, z), z = fmaf(w[2], p.z, z);
+        z = fmaf(w[3], q.x, z), z = fmaf(w[4], q.y, z), z = fmaf(w[5], q.z, z);
+        z = fmaf(w[6], q.w, z);
+        v = lrelu(z, kLReluSlope);
+      }
+      F[g * CSTRIDE + (e % KT) * C + H + m] = v;
+    }
+  } else {
+    for (int m = tid; m < H; m += THREADS) {
+      float w[7];
+#pragma unroll
+      for (int t = 0; t < 7; ++t) w[t] = __ldg(enc_w + m * 7 + t);
+      const float b = __ldg(enc_b + m);
+      for (int e = 0; e < EDGES; ++e) {
+        const int g = e / KT;
+        float v = 0.f;
+        if (NB[e] >= 0) {
+          const float4 p = P[g], q = Q[e];
+          float z = b;
+          z = fmaf(w[0], p.x, z), z = fmaf(w[1], p.y, z), z = fmaf(w[2], p.z, z);
+          z = fmaf(w[3], q.x, z), z = fmaf(w[4], q.y, z), z = fmaf(w[5], q.z, z);
+          z = fmaf(w[6], q.w, z);
+          v = lrelu(z, kLReluSlope);
+        }
+        F[g * CSTRIDE + (e % KT) * C + H + m] = v;
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// acc[k][cw] += sum_r A[k][r] * B[r][col0 + cw],  A = this centre's KT x C block in shared memory,
+// B = [C][C] row-major in global memory (L1/L2 resident), columns col0.. owned by this thread.
+template <class Cfg>
+__device__ __forceinline__ void centre_gemm(float (&acc)[Cfg::KT][Cfg::CW], const float* __restrict__ A,
+                                            const float* __restrict__ B, int col0) {
+  constexpr int C = Cfg::C, KT = Cfg::KT, CW = Cfg::CW;
+#pragma unroll 1
+  for (int r0 = 0; r0 < C; r0 += 4) {
+    float b[4][CW];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) ldg_vec<CW>(b[u], B + (int64_t)(r0 + u) * C + col0);
+#pragma unroll
+    for (int k = 0; k < KT; ++k) {
+      const float4 a = *reinterpret_cast<const float4*>(A + k * C + r0);
+#pragma unroll
+      for (int cw = 0; cw < CW; ++cw) {
+        float v = acc[k][cw];
+        v = fmaf(a.x, b[0][cw], v);
+        v = fmaf(a.y, b[1][cw], v);
+        v = fmaf(a.z, b[2][cw], v);
+        v = fmaf(a.w, b[3][cw], v);
+        acc[k][cw] = v;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------
+template <class Cfg>
+__global__ void __launch_bounds__(Cfg::THREADS, 1)
+lfa_fwd_kernel(const float* __restrict__ x, const float* __restrict__ pos, const int32_t* __restrict__ nbr,
+               const float* __restrict__ enc_w, const float* __restrict__ enc_b,
+               const float* __restrict__ att_wt, float* __restrict__ out, int64_t n, int64_t ntiles) {
+  constexpr int C = Cfg::C, KT = Cfg::KT, CW = Cfg::CW, TC = Cfg::TC, TPC = Cfg::TPC;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* F = reinterpret_cast<float*>(smem_raw);
+  float4* Q = reinterpret_cast<float4*>(F + Cfg::TILE_FLOATS);
+  float4* P = Q + Cfg::EDGES;
+  int* NB = reinterpret_cast<int*>(P + TC);
+
+  const int tid = threadIdx.x;
+  const int g = tid / TPC, col0 = (tid % TPC) * CW;
+
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t tile_base = tile * TC;
+    lfa_build_tile<Cfg>(tile_base, n, x, pos, nbr, enc_w, enc_b, F, Q, P, NB);
+
+    float acc[KT][CW];
+#pragma unroll
+    for (int k = 0; k < KT; ++k)
+#pragma unroll
+      for (int cw = 0; cw < CW; ++cw) acc[k][cw] = 0.f;
+    const float* Fg = F + g * Cfg::CSTRIDE;
+    centre_gemm<Cfg>(acc, Fg, att_wt, col0);
+
+    int deg = 0;
+#pragma unroll
+    for (int k = 0; k < KT; ++k) deg += (NB[g * KT + k] >= 0) ? 1 : 0;
+
+    float mx[CW], sum[CW], o[CW];
+#pragma unroll
+    for (int cw = 0; cw < CW; ++cw) mx[cw] = -CUDART_INF_F, sum[cw] = 0.f, o[cw] = 0.f;
+#pragma unroll
+    for (int k = 0; k < KT; ++k)
+      if (k < deg) {
+#pragma unroll
+        for (int cw = 0; cw < CW; ++cw) mx[cw] = fmaxf(mx[cw], acc[k][cw]);
+      }
+#pragma unroll
+    for (int k = 0; k < KT; ++k)
+      if (k < deg) {
+        float f[CW];
+        load_vec<CW>(f, Fg + k * C + col0);
+#pragma unroll
+        for (int cw = 0; cw < CW; ++cw) {
+          const float p = __expf(acc[k][cw] - mx[cw]);
+          sum[cw] += p;
+          o[cw] = fmaf(p, f[cw], o[cw]);
+        }
+      }
+    const int64_t i = tile_base + g;
+    if (i < n) {
+#pragma unroll
+      for (int cw = 0; cw < CW; ++cw) o[cw] = o[cw] / (sum[cw] + 1e-16f);
+      store_vec<CW>(out + i * C + col0, o);
+    }
+    __syncthreads();  // tile buffers are rebuilt next iteration
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------
+template <class Cfg>
+struct LfaBwdPlan {
+  static constexpr int C = Cfg::C, THREADS = Cfg::THREADS;
+  static constexpr int NB4 = C / 4;                  // 4x4 output blocks per dimension
+  static constexpr int NBLOCKS = NB4 * NB4;
+  static constexpr int SLICES = (NBLOCKS >= THREADS) ? 1 : (THREADS / NBLOCKS);  // edge slices per block
+  static constexpr int PASSES = (NBLOCKS >= THREADS) ? (NBLOCKS / THREADS) : 1;
+  static constexpr bool PERSIST = PASSES <= 2;       // keep dW partials in registers across tiles
+  static_assert(SLICES <= 32 && (SLICES & (SLICES - 1)) == 0, "slices must be a power of two <= 32");
+  static_assert(NBLOCKS >= THREADS ? (NBLOCKS % THREADS == 0) : (THREADS % NBLOCKS == 0), "GEMM3 mapping");
+};
+
+template <class Cfg>
+__global__ void __launch_bounds__(Cfg::THREADS, 1)
+lfa_bwd_kernel(const float* __restrict__ x, const float* __restrict__ pos, const int32_t* __restrict__ nbr,
+               const float* __restrict__ enc_w, const float* __restrict__ enc_b,
+               const float* __restrict__ att_wt, const float* __restrict__ att_w,
+               const float* __restrict__ grad_out, float* __restrict__ grad_x, float* __restrict__ grad_enc_w,
+               float* __restrict__ grad_enc_b, float* __restrict__ grad_att_w, int64_t n, int64_t ntiles) {
+  constexpr int C = Cfg::C, KT = Cfg::KT, CW = Cfg::CW, TC = Cfg::TC, TPC = Cfg::TPC, H = Cfg::H;
+  constexpr int THREADS = Cfg::THREADS, EDGES = Cfg::EDGES, CSTRIDE = Cfg::CSTRIDE;
+  using Plan = LfaBwdPlan<Cfg>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* F = reinterpret_cast<float*>(smem_raw);
+  float* DA = F + Cfg::TILE_FLOATS;
+  float4* Q = reinterpret_cast<float4*>(DA + Cfg::TILE_FLOATS);
+  float4* P = Q + EDGES;
+  int* NB = reinterpret_cast<int*>(P + TC);
+  float* GE = reinterpret_cast<float*>(NB + EDGES);  // [H][8]: 7 weight grads + bias grad
+
+  const int tid = threadIdx.x;
+  const int g = tid / TPC, col0 = (tid % TPC) * CW;
+
+  for (int t = tid; t < H * 8; t += THREADS) GE[t] = 0.f;
+
+  float dw[Plan::PERSIST ? Plan::PASSES : 1][16];
+#pragma unroll
+  for (int p = 0; p < (Plan::PERSIST ? Plan::PASSES : 1); ++p)
+#pragma unroll
+    for (int t = 0; t < 16; ++t) dw[p][t] = 0.f;
+
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t tile_base = tile * TC;
+    lfa_build_tile<Cfg>(tile_base, n, x, pos, nbr, enc_w, enc_b, F, Q, P, NB);
+
+    float acc[KT][CW];
+#pragma unroll
+    for (int k = 0; k < KT; ++k)
+#pragma unroll
+      for (int cw = 0; cw < CW; ++cw) acc[k][cw] = 0.f;
+    const float* Fg = F + g * CSTRIDE;
+    float* DAg = DA + g * CSTRIDE;
+    centre_gemm<Cfg>(acc, Fg, att_wt, col0);
+
+    int deg = 0;
+#pragma unroll
+    for (int k = 0; k < KT; ++k) deg += (NB[g * KT + k] >= 0) ? 1 : 0;
+    const int64_t i = tile_base + g;
+
+    {  // softmax backward: acc <- s*go (direct term of dF), DA <- s*go*(f - o)
+      float mx[CW], sum[CW], o[CW], go[CW];
+#pragma unroll
+      for (int cw = 0; cw < CW; ++cw) mx[cw] = -CUDART_INF_F, sum[cw] = 0.f, o[cw] = 0.f, go[cw] = 0.f;
+      if (i < n) ldg_vec<CW>(go, grad_out + i * C + col0);
+#pragma unroll
+      for (int k = 0; k < KT; ++k)
+        if (k < deg) {
+#pragma unroll
+          for (int cw = 0; cw < CW; ++cw) mx[cw] = fmaxf(mx[cw], acc[k][cw]);
+        }
+#pragma unroll
+      for (int k = 0; k < KT; ++k)
+        if (k < deg) {
+          float f[CW];
+          load_vec<CW>(f, Fg + k * C + col0);
+#pragma unroll
+          for (int cw = 0; cw < CW; ++cw) {
+            const float p = __expf(acc[k][cw] - mx[cw]);
+            acc[k][cw] = p;
+            sum[cw] += p;
+            o[cw] = fmaf(p, f[cw], o[cw]);
+          }
+        }
+      float inv[CW];
+#pragma unroll
+      for (int cw = 0; cw < CW; ++cw) {
+        inv[cw] = 1.f / (sum[cw] + 1e-16f);
+        o[cw] *= inv[cw];
+      }
+#pragma unroll
+      for (int k = 0; k < KT; ++k) {
+        float da[CW];
+        if (k < deg) {
+          float f[CW];
+          load_vec<CW>(f, Fg + k * C + col0);
+#pragma unroll
+          for (int cw = 0; cw < CW; ++cw) {
+            const float sg = acc[k][cw] * inv[cw] * go[cw];
+            acc[k][cw] = sg;
+            da[cw] = sg * (f[cw] - o[cw]);
+          }
+        } else {
+#pragma unroll
+          for (int cw = 0; cw < CW; ++cw) {
+            acc[k][cw] = 0.f;
+            da[cw] = 0.f;
+          }
+        }
+        store_vec<CW>(DAg + k * C + col0, da);
+      }
+    }
+    __syncthreads();
+
+    // GEMM2: dF[k][m] = sg[k][m] + sum_n DA[k][n] W[n][m]   (acc already holds sg)
+    centre_gemm<Cfg>(acc, DAg, att_w, col0);
+
+    if (col0 < H) {
+      // gradient w.r.t. the gathered neighbour features
+#pragma unroll
+      for (int k = 0; k < KT; ++k)
+        if (k < deg) {
+          const int j = NB[g * KT + k];
+          red_vec<CW>(grad_x + (int64_t)j * H + col0, acc[k]);
+        }
+    } else {
+      // gradient w.r.t. the (folded) encoder: dz = dF * lrelu'(z), sign(z) = sign(e)
+      const float4 p = P[g];
+#pragma unroll
+      for (int cw = 0; cw < CW; ++cw) {
+        float gw[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) gw[t] = 0.f;
+#pragma unroll
+        for (int k = 0; k < KT; ++k)
+          if (k < deg) {
+            const float e = Fg[k * C + col0 + cw];
+            const float dz = acc[k][cw] * (e > 0.f ? 1.f : kLReluSlope);
+            const float4 q = Q[g * KT + k];
+            gw[3] = fmaf(dz, q.x, gw[3]);
+            gw[4] = fmaf(dz, q.y, gw[4]);
+            gw[5] = fmaf(dz, q.z, gw[5]);
+            gw[6] = fmaf(dz, q.w, gw[6]);
+            gw[7] += dz;
+          }
+        gw[0] = gw[7] * p.x, gw[1] = gw[7] * p.y, gw[2] = gw[7] * p.z;
+        float* ge = GE + (col0 - H + cw) * 8;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) atomicAdd(ge + t, gw[t]);
+      }
+    }
+
+    // GEMM3: dW[n][m] += sum_e DA[e][n] F[e][m], 4x4 register blocks
+#pragma unroll
+    for (int pass = 0; pass < Plan::PASSES; ++pass) {
+      const int ob = (Plan::SLICES > 1) ? (tid / Plan::SLICES) : (pass * THREADS + tid);
+      const int es = (Plan::SLICES > 1) ? (tid % Plan::SLICES) : 0;
+      const int nb = ob / Plan::NB4, mb = ob % Plan::NB4;
+      float part[16];
+#pragma unroll
+      for (int t = 0; t < 16; ++t) part[t] = Plan::PERSIST ? dw[Plan::PERSIST ? pass : 0][t] : 0.f;
+#pragma unroll 4
+      for (int e = es; e < EDGES; e += Plan::SLICES) {
+        const int off = (e / KT) * CSTRIDE + (e % KT) * C;
+        const float4 a = *reinterpret_cast<const float4*>(DA + off + nb * 4);
+        const float4 b = *reinterpret_cast<const float4*>(F + off + mb * 4);
+        const float av[4] = {a.x, a.y, a.z, a.w};
+        const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int s = 0; s < 4; ++s) part[r * 4 + s] = fmaf(av[r], bv[s], part[r * 4 + s]);
+      }
+      if constexpr (Plan::PERSIST) {
+#pragma unroll
+        for (int t = 0; t < 16; ++t) dw[pass][t] = part[t];
+      } else {
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+          atomicAdd(reinterpret_cast<float4*>(grad_att_w + (int64_t)(nb * 4 + r) * C + mb * 4),
+                    make_float4(part[r * 4 + 0], part[r * 4 + 1], part[r * 4 + 2], part[r * 4 + 3]));
+      }
+    }
+    __syncthreads();  // tile buffers are rebuilt next iteration
+  }
+
+  // flush the per-CTA partial gradients
+  if constexpr (Plan::PERSIST) {
+#pragma unroll
+    for (int pass = 0; pass < Plan::PASSES; ++pass) {
+      const int ob = (Plan::SLICES > 1) ? (tid / Plan::SLICES) : (pass * THREADS + tid);
+      const int es = (Plan::SLICES > 1) ? (tid % Plan::SLICES) : 0;
+      const int nb = ob / Plan::NB4, mb = ob % Plan::NB4;
+#pragma unroll
+      for (int t = 0; t < 16; ++t) {
+        float v = dw[pass][t];
+#pragma unroll
+        for (int o = Plan::SLICES / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        dw[pass][t] = v;
+      }
+      if (es == 0) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+          atomicAdd(reinterpret_cast<float4*>(grad_att_w + (int64_t)(nb * 4 + r) * C + mb * 4),
+                    make_float4(dw[pass][r * 4 + 0], dw[pass][r * 4 + 1], dw[pass][r * 4 + 2], dw[pass][r * 4 + 3]));
+      }
+    }
+  }
+  __syncthreads();
+  for (int t = tid; t < H * 8; t += THREADS) {
+    const float v = GE[t];
+    const int m = t >> 3, s = t & 7;
+    if (s < 7)
+      atomicAdd(grad_enc_w + m * 7 + s, v);
+    else
+      atomicAdd(grad_enc_b + m, v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// dispatch
+// ------------------------------------------------------------------------------------------
+template <class Cfg>
+static size_t lfa_fwd_smem() {
+  return sizeof(float) * Cfg::TILE_FLOATS + sizeof(float4) * (Cfg::EDGES + Cfg::TC) + sizeof(int) * Cfg::EDGES;
+}
+template <class Cfg>
+static size_t lfa_bwd_smem() {
+  return sizeof(float) * 2 * Cfg::TILE_FLOATS + sizeof(float4) * (Cfg::EDGES + Cfg::TC) + sizeof(int) * Cfg::EDGES +
+         sizeof(float) * Cfg::H * 8;
+}
+
+static int persistent_grid(const void* kernel, int threads, size_t smem, int64_t ntiles) {
+  int per_sm = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess || per_sm < 1) {
+    cudaGetLastError();
+    per_sm = 1;
+  }
+  int64_t g = (int64_t)num_sms() * per_sm;
+  if (g > ntiles) g = ntiles;
+  return (int)(g < 1 ? 1 : g);
+}
+
+template <class Cfg>
+static int launch_lfa_fwd(const float* x, const float* pos, const int32_t* nbr, const float* enc_w,
+                          const float* enc_b, const float* att_wt, float* out, int64_t n, cudaStream_t st) {
+  const size_t smem = lfa_fwd_smem<Cfg>();
+  auto kern = lfa_fwd_kernel<Cfg>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return cuda_fail(e, "lfa_fwd smem attribute");
+  const int64_t ntiles = ceil_div(n, Cfg::TC);
+  const int grid = persistent_grid(reinterpret_cast<const void*>(kern), Cfg::THREADS, smem, ntiles);
+  kern<<<grid, Cfg::THREADS, smem, st>>>(x, pos, nbr, enc_w, enc_b, att_wt, out, n, ntiles);
+  B200_CHECK_LAUNCH("lfa_fwd_kernel");
+  return B200_OK;
+}
+
+template <class Cfg>
+static int launch_lfa_bwd(const float* x, const float* pos, const int32_t* nbr, const float* enc_w,
+                          const float* enc_b, const float* att_wt, const float* att_w, const float* go, float* gx,
+                          float* gew, float* geb, float* gaw, int64_t n, cudaStream_t st) {
+  const size_t smem = lfa_bwd_smem<Cfg>();
+  auto kern = lfa_bwd_kernel<Cfg>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return cuda_fail(e, "lfa_bwd smem attribute");
+  const int64_t ntiles = ceil_div(n, Cfg::TC);
+  const int grid = persistent_grid(reinterpret_cast<const void*>(kern), Cfg::THREADS, smem, ntiles);
+  kern<<<grid, Cfg::THREADS, smem, st>>>(x, pos, nbr, enc_w, enc_b, att_wt, att_w, go, gx, gew, geb, gaw, n, ntiles);
+  B200_CHECK_LAUNCH("lfa_bwd_kernel");
+  return B200_OK;
+}
+
+}  // namespace b200
+
+extern "C" int b200_edge_moments(const float* pos, const int32_t* nbr, int64_t n, int32_t kt, double* out,
+                                 void* stream) {
+  using namespace b200;
+  B200_REQUIRE(pos && nbr && out, B200_E_INVALID, "b200_edge_moments: null pointer");
+  B200_REQUIRE(kt >= 1, B200_E_INVALID, "b200_edge_moments: kt=%d", kt);
+  if (n <= 0) return B200_OK;
+  int64_t blocks = ceil_div(n, MOM_THREADS);
+  const int64_t cap = (int64_t)num_sms() * 4;
+  if (blocks > cap) blocks = cap;
+  edge_moments_kernel<<<(unsigned)blocks, MOM_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(pos, nbr, n, kt, out);
+  B200_CHECK_LAUNCH("edge_moments_kernel");
+  return B200_OK;
+}
+
+// (C, KT) -> (CW, TC) tables; see the header comment for the reasoning.
+#define B200_LFA_FWD_CASES(X) \
+  X(8, 16, 2, 32) X(16, 16, 4, 32) X(32, 16, 4, 16) X(64, 16, 8, 16) X(128, 16, 8, 8) X(256, 16, 8, 8) \
+  X(8, 32, 2, 32) X(16, 32, 4, 32) X(32, 32, 4, 16) X(64, 32, 4, 8) X(128, 32, 4, 4) X(256, 32, 4, 4)
+#define B200_LFA_BWD_CASES(X) \
+  X(8, 16, 2, 32) X(16, 16, 4, 32) X(32, 16, 4, 16) X(64, 16, 8, 16) X(128, 16, 8, 8) X(256, 16, 8, 4) \
+  X(8, 32, 2, 32) X(16, 32, 4, 32) X(32, 32, 4, 16) X(64, 32, 4, 8) X(128, 32, 4, 4) X(256, 32, 4, 2)
+
+extern "C" int b200_lfa_fwd(const float* x, const float* pos, const int32_t* nbr, const float* enc_w,
+                            const float* enc_b, const float* att_wt, float* out, int64_t n, int32_t c, int32_t kt,
+                            void* stream) {
+  using namespace b200;
+  B200_REQUIRE(x && pos && nbr && enc_w && enc_b && att_wt && out, B200_E_INVALID, "b200_lfa_fwd: null pointer");
+  B200_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)att_wt & 15) == 0 && ((uintptr_t)out & 15) == 0, B200_E_INVALID,
+               "b200_lfa_fwd: x, att_wt and out must be 16-byte aligned");
+  if (n <= 0) return B200_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define X(C_, KT_, CW_, TC_) \
+  if (c == C_ && kt == KT_) return launch_lfa_fwd<LfaCfg<C_, KT_, CW_, TC_>>(x, pos, nbr, enc_w, enc_b, att_wt, out, n, st);
+  B200_LFA_FWD_CASES(X)
+#undef X
+  set_error("b200_lfa_fwd: unsupported (c=%d, kt=%d); c in {8,16,32,64,128,256}, kt in {16,32}", c, kt);
+  return B200_E_UNSUPPORTED;
+}
+
+extern "C" int b200_lfa_bwd(const float* x, const float* pos, const int32_t* nbr, const float* enc_w,
+                            const float* enc_b, const float* att_wt, const float* att_w, const float* grad_out,
+                            float* grad_x, float* grad_enc_w, float* grad_enc_b, float* grad_att_w, int64_t n,
+                            int32_t c, int32_t kt, void* stream) {
+  using namespace b200;
+  B200_REQUIRE(x && pos && nbr && enc_w && enc_b && att_wt && att_w && grad_out && grad_x && grad_enc_w &&
+                   grad_enc_b && grad_att_w,
+               B200_E_INVALID, "b200_lfa_bwd: null pointer");
+  B200_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)att_wt & 15) == 0 && ((uintptr_t)att_w & 15) == 0 &&
+                   ((uintptr_t)grad_out & 15) == 0 && ((uintptr_t)grad_x & 15) == 0 && ((uintptr_t)grad_att_w & 15) == 0,
+               B200_E_INVALID, "b200_lfa_bwd: tensors must be 16-byte aligned");
+  if (n <= 0) return B200_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define X(C_, KT_, CW_, TC_)                                                                                    \
+  if (c == C_ && kt == KT_)                                                                                     \
+    return launch_lfa_bwd<LfaCfg<C_, KT_, CW_, TC_>>(x, pos, nbr, enc_w, enc_b, att_wt, att_w, grad_out, grad_x, \
+                                                     grad_enc_w, grad_enc_b, grad_att_w, n, st);
+  B200_LFA_BWD_CASES(X)
+#undef X
+  set_error("b200_lfa_bwd: unsupported (c=%d, kt=%d); c in {8,16,32,64,128,256}, kt in {16,32}", c, kt);
+  return B200_E_UNSUPPORTED;
+}

@@ -1,0 +1,642 @@
+// Per-point shared-MLP kernels for sm_100a: Linear (forward, input-gradient, weight-gradient) with a
+// concatenated two-segment input and a BatchNorm-statistics epilogue, BatchNorm finalisation and
+// the fused affine + LeakyReLU (+ residual branch) forward / backward passes.
+//
+// Replaces SharedMLP = PyG MLP (myria3d/models/modules/pyg_randla_net.py:97-109), fc0 / fc_classif
+// (:42,:53), the torch.cat of FPModule (:251) and the block tail lrelu(mlp2(x) + shortcut(x)) (:186-187);
+// in the reference each layer is cuBLAS SGEMM + 2 BatchNorm passes + an activation pass.
+//
+// The contractions here are fp32 FMA register-tiled (64x64 or 128x32 CTA tiles, 16-deep k slices).
+// TODO(round 2): tcgen05 TF32x3 tiles for the cout >= 64 layers.
+#include "common.cuh"
+
+namespace b200 {
+
+constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_BK = 16;
+
+// one row of the (virtually concatenated) activation matrix [a1 | a2]
+struct CatRows {
+  const float* a1;
+  int64_t ld1;
+  int c1;
+  const float* a2;
+  int64_t ld2;
+  int c2;
+  bool vec;  // every row segment is float4-addressable
+};
+
+__device__ __forceinline__ float cat_load1(const CatRows& A, int64_t row, int k) {
+  if (k < A.c1) return __ldg(A.a1 + row * A.ld1 + k);
+  if (k < A.c1 + A.c2) return __ldg(A.a2 + row * A.ld2 + (k - A.c1));
+  return 0.f;
+}
+__device__ __forceinline__ float4 cat_load4(const CatRows& A, int64_t row, int k) {
+  if (A.vec) {
+    if (k < A.c1) return __ldg(reinterpret_cast<const float4*>(A.a1 + row * A.ld1 + k));
+    if (k < A.c1 + A.c2) return __ldg(reinterpret_cast<const float4*>(A.a2 + row * A.ld2 + (k - A.c1)));
+    return make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  return make_float4(cat_load1(A, row, k), cat_load1(A, row, k + 1), cat_load1(A, row, k + 2), cat_load1(A, row, k + 3));
+}
+
+// dense row-major matrix [rows, cols] (ld = cols)
+__device__ __forceinline__ float4 dense_load4(const float* __restrict__ p, int64_t rows, int cols, bool vec, int64_t r,
+                                              int c) {
+  if (r >= rows) return make_float4(0.f, 0.f, 0.f, 0.f);
+  const float* q = p + r * cols + c;
+  if (vec && c + 3 < cols) return __ldg(reinterpret_cast<const float4*>(q));
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c + 0 < cols) v.x = __ldg(q + 0);
+  if (c + 1 < cols) v.y = __ldg(q + 1);
+  if (c + 2 < cols) v.z = __ldg(q + 2);
+  if (c + 3 < cols) v.w = __ldg(q + 3);
+  return v;
+}
+
+template <int BM, int BN>
+struct GemmTile {
+  static constexpr int TM = BM / 16, TN = BN / 16;
+  static_assert(BM % 16 == 0 && BN % 16 == 0, "tile");
+  float acc[TM][TN];
+  __device__ __forceinline__ void zero() {
+#pragma unroll
+    for (int r = 0; r < TM; ++r)
+#pragma unroll
+      for (int s = 0; s < TN; ++s) acc[r][s] = 0.f;
+  }
+  // As[kk][row], Bs[kk][col]
+  __device__ __forceinline__ void mac(const float (*As)[BM + 4], const float (*Bs)[BN + 4], int ty, int tx) {
+#pragma unroll
+    for (int kk = 0; kk < GEMM_BK; ++kk) {
+      float a[TM], b[TN];
+#pragma unroll
+      for (int r = 0; r < TM; ++r) a[r] = As[kk][ty * TM + r];
+#pragma unroll
+      for (int s = 0; s < TN; ++s) b[s] = Bs[kk][tx * TN + s];
+#pragma unroll
+      for (int r = 0; r < TM; ++r)
+#pragma unroll
+        for (int s = 0; s < TN; ++s) acc[r][s] = fmaf(a[r], b[s], acc[r][s]);
+    }
+  }
+};
+
+// ------------------------------------------------------------------ y = [a1|a2] W^T + bias
+template <int BM, int BN>
+__global__ void __launch_bounds__(GEMM_THREADS)
+linear_fwd_kernel(CatRows A, const float* __restrict__ w, bool wvec, const float* __restrict__ bias,
+                  float* __restrict__ y, int64_t n, int cout, double* __restrict__ colstats) {
+  __shared__ __align__(16) float As[GEMM_BK][BM + 4];
+  __shared__ __align__(16) float Bs[GEMM_BK][BN + 4];
+  __shared__ double cs[2][BN];
+  const int tid = threadIdx.x, ty = tid / 16, tx = tid % 16;
+  const int64_t row0 = (int64_t)blockIdx.x * BM;
+  const int col0 = blockIdx.y * BN;
+  const int ktot = A.c1 + A.c2;
+  GemmTile<BM, BN> T;
+  T.zero();
+  if (colstats)
+    for (int t = tid; t < 2 * BN; t += GEMM_THREADS) (&cs[0][0])[t] = 0.0;
+
+  for (int k0 = 0; k0 < ktot; k0 += GEMM_BK) {
+    for (int s = tid; s < BM * 4; s += GEMM_THREADS) {
+      const int r = s >> 2, kq = s & 3;
+      const int64_t row = row0 + r;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row < n) v = cat_load4(A, row, k0 + kq * 4);
+      As[kq * 4 + 0][r] = v.x, As[kq * 4 + 1][r] = v.y, As[kq * 4 + 2][r] = v.z, As[kq * 4 + 3][r] = v.w;
+    }
+    for (int s = tid; s < BN * 4; s += GEMM_THREADS) {
+      const int r = s >> 2, kq = s & 3;
+      const float4 v = dense_load4(w, cout, ktot, wvec, col0 + r, k0 + kq * 4);
+      Bs[kq * 4 + 0][r] = v.x, Bs[kq * 4 + 1][r] = v.y, Bs[kq * 4 + 2][r] = v.z, Bs[kq * 4 + 3][r] = v.w;
+    }
+    __syncthreads();
+    T.mac(As, Bs, ty, tx);
+    __syncthreads();
+  }
+
+  constexpr int TM = GemmTile<BM, BN>::TM, TN = GemmTile<BM, BN>::TN;
+  // BatchNorm statistics in fp64: var = E[y^2] - E[y]^2 cancels catastrophically in fp32 when
+  // |mean| >> std (e.g. the 2-row batches of tiny clouds), and fp32 x fp32 products are exact in fp64
+  double psum[TN], psq[TN];
+#pragma unroll
+  for (int s = 0; s < TN; ++s) psum[s] = 0.0, psq[s] = 0.0;
+#pragma unroll
+  for (int r = 0; r < TM; ++r) {
+    const int64_t row = row0 + ty * TM + r;
+    if (row >= n) continue;
+#pragma unroll
+    for (int s = 0; s < TN; ++s) {
+      const int col = col0 + tx * TN + s;
+      if (col < cout) {
+        const float v = T.acc[r][s] + (bias ? __ldg(bias + col) : 0.f);
+        y[row * cout + col] = v;
+        if (colstats) {
+          psum[s] += (double)v;
+          psq[s] = fma((double)v, (double)v, psq[s]);
+        }
+      }
+    }
+  }
+  if (colstats) {
+#pragma unroll
+    for (int s = 0; s < TN; ++s) {
+      atomicAdd(&cs[0][tx * TN + s], psum[s]);
+      atomicAdd(&cs[1][tx * TN + s], psq[s]);
+    }
+    __syncthreads();
+    for (int t = tid; t < BN; t += GEMM_THREADS) {
+      const int col = col0 + t;
+      if (col < cout) {
+        atomicAdd(colstats + col, cs[0][t]);
+        atomicAdd(colstats + cout + col, cs[1][t]);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ [ga1|ga2] = gy W
+template <int BM, int BN>
+__global__ void __launch_bounds__(GEMM_THREADS)
+linear_bwd_input_kernel(const float* __restrict__ gy, bool gvec, const float* __restrict__ w, bool wvec,
+                        float* __restrict__ ga1, int64_t ldg1, int c1, float* __restrict__ ga2, int64_t ldg2, int c2,
+                        int64_t n, int cout) {
+  __shared__ __align__(16) float As[GEMM_BK][BM + 4];
+  __shared__ __align__(16) float Bs[GEMM_BK][BN + 4];
+  const int tid = threadIdx.x, ty = tid / 16, tx = tid % 16;
+  const int64_t row0 = (int64_t)blockIdx.x * BM;
+  const int col0 = blockIdx.y * BN;
+  const int ktot = c1 + c2;
+  GemmTile<BM, BN> T;
+  T.zero();
+
+  for (int k0 = 0; k0 < cout; k0 += GEMM_BK) {
+    for (int s = tid; s < BM * 4; s += GEMM_THREADS) {
+      const int r = s >> 2, kq = s & 3;
+      const float4 v = dense_load4(gy, n, cout, gvec, row0 + r, k0 + kq * 4);
+      As[kq * 4 + 0][r] = v.x, As[kq * 4 + 1][r] = v.y, As[kq * 4 + 2][r] = v.z, As[kq * 4 + 3][r] = v.w;
+    }
+    for (int s = tid; s < GEMM_BK * (BN / 4); s += GEMM_THREADS) {
+      const int kk = s / (BN / 4), cq = s % (BN / 4);
+      const float4 v = dense_load4(w, cout, ktot, wvec, k0 + kk, col0 + cq * 4);
+      *reinterpret_cast<float4*>(&Bs[kk][cq * 4]) = v;
+    }
+    __syncthreads();
+    T.mac(As, Bs, ty, tx);
+    __syncthreads();
+  }
+
+  constexpr int TM = GemmTile<BM, BN>::TM, TN = GemmTile<BM, BN>::TN;
+#pragma unroll
+  for (int r = 0; r < TM; ++r) {
+    const int64_t row = row0 + ty * TM + r;
+    if (row >= n) continue;
+#pragma unroll
+    for (int s = 0; s < TN; ++s) {
+      const int col = col0 + tx * TN + s;
+      if (col < c1) {
+        if (ga1) ga1[row * ldg1 + col] = T.acc[r][s];
+      } else if (col < ktot) {
+        if (ga2) ga2[row * ldg2 + (col - c1)] = T.acc[r][s];
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ gw += gy^T [a1|a2], gb += colsum(gy)
+// The bias gradient rides along as one extra "ones" column of the activation matrix.
+template <int BM, int BN>
+__global__ void __launch_bounds__(GEMM_THREADS)
+linear_bwd_weight_kernel(const float* __restrict__ gy, bool gvec, CatRows A, float* __restrict__ gw,
+                         float* __restrict__ gb, int64_t n, int cout, int64_t rows_per_split) {
+  __shared__ __align__(16) float As[GEMM_BK][BM + 4];  // As[kk][m] = gy[i0+kk][m0+m]
+  __shared__ __align__(16) float Bs[GEMM_BK][BN + 4];  // Bs[kk][c] = A[i0+kk][c0+c]
+  const int tid = threadIdx.x, ty = tid / 16, tx = tid % 16;
+  const int m0 = blockIdx.x * BM;
+  const int c0 = blockIdx.y * BN;
+  const int ktot = A.c1 + A.c2;
+  const int ncols = ktot + (gb ? 1 : 0);
+  const int64_t i_begin = (int64_t)blockIdx.z * rows_per_split;
+  const int64_t i_end = (i_begin + rows_per_split < n) ? (i_begin + rows_per_split) : n;
+  GemmTile<BM, BN> T;
+  T.zero();
+
+  for (int64_t i0 = i_begin; i0 < i_end; i0 += GEMM_BK) {
+    for (int s = tid; s < GEMM_BK * (BM / 4); s += GEMM_THREADS) {
+      const int kk = s / (BM / 4), mq = s % (BM / 4);
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i0 + kk < i_end) v = dense_load4(gy, n, cout, gvec, i0 + kk, m0 + mq * 4);
+      *reinterpret_cast<float4*>(&As[kk][mq * 4]) = v;
+    }
+    for (int s = tid; s < GEMM_BK * (BN / 4); s += GEMM_THREADS) {
+      const int kk = s / (BN / 4), cq = s % (BN / 4);
+      const int c = c0 + cq * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i0 + kk < i_end) {
+        if (c + 3 < ktot) {
+          v = cat_load4(A, i0 + kk, c);
+        } else {
+          float e[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int cc = c + u;
+            e[u] = (cc < ktot) ? cat_load1(A, i0 + kk, cc) : ((cc == ktot && gb) ? 1.f : 0.f);
+          }
+          v = make_float4(e[0], e[1], e[2], e[3]);
+        }
+      }
+      *reinterpret_cast<float4*>(&Bs[kk][cq * 4]) = v;
+    }
+    __syncthreads();
+    T.mac(As, Bs, ty, tx);
+    __syncthreads();
+  }
+
+  constexpr int TM = GemmTile<BM, BN>::TM, TN = GemmTile<BM, BN>::TN;
+#pragma unroll
+  for (int r = 0; r < TM; ++r) {
+    const int m = m0 + ty * TM + r;
+    if (m >= cout) continue;
+#pragma unroll
+    for (int s = 0; s < TN; ++s) {
+      const int c = c0 + tx * TN + s;
+      if (c < ktot)
+        atomicAdd(gw + (int64_t)m * ktot + c, T.acc[r][s]);
+      else if (c < ncols)
+        atomicAdd(gb + m, T.acc[r][s]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ BatchNorm finalisation
+__global__ void bn_finalize_kernel(const double* __restrict__ colstats, int64_t count, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* __restrict__ running_mean,
+                                   float* __restrict__ running_var, float momentum, float eps,
+                                   float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
+                                   float* __restrict__ invstd_out, int c) {
+  for (int ch = blockIdx.x * blockDim.x + threadIdx.x; ch < c; ch += gridDim.x * blockDim.x) {
+    double mean, var;
+    if (colstats) {
+      mean = colstats[ch] / (double)count;
+      var = colstats[c + ch] / (double)count - mean * mean;
+      if (var < 0.0) var = 0.0;
+      if (running_mean) {
+        const double unbiased = (count > 1) ? var * (double)count / (double)(count - 1) : var;
+        running_mean[ch] = (float)((1.0 - (double)momentum) * (double)running_mean[ch] + (double)momentum * mean);
+        running_var[ch] = (float)((1.0 - (double)momentum) * (double)running_var[ch] + (double)momentum * unbiased);
+      }
+    } else {
+      mean = (double)running_mean[ch];
+      var = (double)running_var[ch];
+    }
+    const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float sc = gamma[ch] * invstd;
+    scale[ch] = sc;
+    shift[ch] = beta[ch] - (float)mean * sc;
+    if (mean_out) mean_out[ch] = (float)mean;
+    if (invstd_out) invstd_out[ch] = invstd;
+  }
+}
+
+// ------------------------------------------------------------------ out = act(y1*s1 + t1 [+ y2*s2 + t2])
+template <int V>
+__global__ void __launch_bounds__(256)
+affine_act_fwd_kernel(const float* __restrict__ y1, const float* __restrict__ s1, const float* __restrict__ t1,
+                      const float* __restrict__ y2, const float* __restrict__ s2, const float* __restrict__ t2,
+                      float slope, float* __restrict__ out, int64_t total, int c) {
+  for (int64_t idx = ((int64_t)blockIdx.x * 256 + threadIdx.x) * V; idx < total; idx += (int64_t)gridDim.x * 256 * V) {
+    const int ch = (int)(idx % c);
+    float a[V], b[V], o[V];
+    if constexpr (V == 4) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(y1 + idx));
+      a[0] = v.x, a[1] = v.y, a[2] = v.z, a[3] = v.w;
+      if (y2) {
+        const float4 u = __ldg(reinterpret_cast<const float4*>(y2 + idx));
+        b[0] = u.x, b[1] = u.y, b[2] = u.z, b[3] = u.w;
+      }
+    } else {
+      a[0] = __ldg(y1 + idx);
+      if (y2) b[0] = __ldg(y2 + idx);
+    }
+#pragma unroll
+    for (int u = 0; u < V; ++u) {
+      float v = fmaf(a[u], __ldg(s1 + ch + u), __ldg(t1 + ch + u));
+      if (y2) v += fmaf(b[u], __ldg(s2 + ch + u), __ldg(t2 + ch + u));
+      o[u] = lrelu(v, slope);
+    }
+    if constexpr (V == 4)
+      *reinterpret_cast<float4*>(out + idx) = make_float4(o[0], o[1], o[2], o[3]);
+    else
+      out[idx] = o[0];
+  }
+}
+
+// ------------------------------------------------------------------ backward reductions
+// red[0:c] = sum_i g, red[c:2c] = sum_i g * xhat,  g = grad_out * act'(out)
+constexpr int RED_THREADS = 256;
+__global__ void __launch_bounds__(RED_THREADS)
+affine_act_bwd_reduce_kernel(const float* __restrict__ go, const float* __restrict__ out, float slope,
+                             const float* __restrict__ y1, const float* __restrict__ mean1,
+                             const float* __restrict__ invstd1, double* __restrict__ red1,
+                             const float* __restrict__ y2, const float* __restrict__ mean2,
+                             const float* __restrict__ invstd2, double* __restrict__ red2, int64_t n, int c,
+                             int lanes /* pow2 >= min(c, 256) */) {
+  extern __shared__ double sred[];  // [4][lanes]
+  const int tid = threadIdx.x;
+  const int lane = tid % lanes, rsub = tid / lanes, rstep = RED_THREADS / lanes;
+  for (int cbase = 0; cbase < c; cbase += lanes) {
+    const int ch = cbase + lane;
+    float sg = 0.f, sgx1 = 0.f, sgx2 = 0.f;
+    if (ch < c) {
+      const float m1 = __ldg(mean1 + ch), is1 = __ldg(invstd1 + ch);
+      const float m2 = y2 ? __ldg(mean2 + ch) : 0.f, is2 = y2 ? __ldg(invstd2 + ch) : 0.f;
+      for (int64_t i = (int64_t)blockIdx.x * rstep + rsub; i < n; i += (int64_t)gridDim.x * rstep) {
+        const int64_t off = i * c + ch;
+        float g = __ldg(go + off);
+        if (slope != 1.f) g *= (__ldg(out + off) > 0.f) ? 1.f : slope;
+        sg += g;
+        sgx1 = fmaf(g, (__ldg(y1 + off) - m1) * is1, sgx1);
+        if (y2) sgx2 = fmaf(g, (__ldg(y2 + off) - m2) * is2, sgx2);
+      }
+    }
+    for (int t = tid; t < 4 * lanes; t += RED_THREADS) sred[t] = 0.0;
+    __syncthreads();
+    if (ch < c) {
+      atomicAdd(&sred[0 * lanes + lane], (double)sg);
+      atomicAdd(&sred[1 * lanes + lane], (double)sgx1);
+      if (y2) atomicAdd(&sred[2 * lanes + lane], (double)sgx2);
+    }
+    __syncthreads();
+    if (tid < lanes && cbase + tid < c) {
+      atomicAdd(red1 + cbase + tid, sred[0 * lanes + tid]);
+      atomicAdd(red1 + c + cbase + tid, sred[1 * lanes + tid]);
+      if (y2) {
+        atomicAdd(red2 + cbase + tid, sred[0 * lanes + tid]);
+        atomicAdd(red2 + c + cbase + tid, sred[2 * lanes + tid]);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+struct BnBranch {
+  const float* y;
+  const float* gamma;
+  const float* mean;
+  const float* invstd;
+  const double* red;   // nullptr => plain affine: grad_y = g * scale
+  const float* scale;
+  float* grad_y;
+  float* grad_gamma;
+  float* grad_beta;
+};
+
+template <int V>
+__global__ void __launch_bounds__(256)
+affine_act_bwd_apply_kernel(const float* __restrict__ go, const float* __restrict__ out, float slope, BnBranch b1,
+                            BnBranch b2, int64_t n, int c) {
+  const int64_t total = n * c;
+  const double inv_n = 1.0 / (double)n;
+  // parameter gradients (train-mode BatchNorm): written once by the first CTA
+  if (blockIdx.x == 0) {
+    for (int ch = threadIdx.x; ch < c; ch += 256) {
+      if (b1.red && b1.grad_gamma) {
+        b1.grad_gamma[ch] = (float)b1.red[c + ch];
+        b1.grad_beta[ch] = (float)b1.red[ch];
+      }
+      if (b2.y && b2.red && b2.grad_gamma) {
+        b2.grad_gamma[ch] = (float)b2.red[c + ch];
+        b2.grad_beta[ch] = (float)b2.red[ch];
+      }
+    }
+  }
+  for (int64_t idx = ((int64_t)blockIdx.x * 256 + threadIdx.x) * V; idx < total; idx += (int64_t)gridDim.x * 256 * V) {
+    const int ch0 = (int)(idx % c);
+    float g[V], o[V], y1v[V], y2v[V];
+    if constexpr (V == 4) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(go + idx));
+      g[0] = a.x, g[1] = a.y, g[2] = a.z, g[3] = a.w;
+      if (slope != 1.f) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(out + idx));
+        o[0] = b.x, o[1] = b.y, o[2] = b.z, o[3] = b.w;
+      }
+      if (b1.red) {
+        const float4 d = __ldg(reinterpret_cast<const float4*>(b1.y + idx));
+        y1v[0] = d.x, y1v[1] = d.y, y1v[2] = d.z, y1v[3] = d.w;
+      }
+      if (b2.y && b2.red) {
+        const float4 d = __ldg(reinterpret_cast<const float4*>(b2.y + idx));
+        y2v[0] = d.x, y2v[1] = d.y, y2v[2] = d.z, y2v[3] = d.w;
+      }
+    } else {
+      g[0] = __ldg(go + idx);
+      if (slope != 1.f) o[0] = __ldg(out + idx);
+      if (b1.red) y1v[0] = __ldg(b1.y + idx);
+      if (b2.y && b2.red) y2v[0] = __ldg(b2.y + idx);
+    }
+    float r1[V], r2[V];
+#pragma unroll
+    for (int u = 0; u < V; ++u) {
+      const int ch = ch0 + u;
+      float gg = g[u];
+      if (slope != 1.f) gg *= (o[u] > 0.f) ? 1.f : slope;
+      if (b1.red) {
+        const float is = __ldg(b1.invstd + ch);
+        const float xh = (y1v[u] - __ldg(b1.mean + ch)) * is;
+        const float mg = (float)(b1.red[ch] * inv_n), mgx = (float)(b1.red[c + ch] * inv_n);
+        r1[u] = __ldg(b1.gamma + ch) * is * (gg - mg - xh * mgx);
+      } else {
+        r1[u] = gg * __ldg(b1.scale + ch);
+      }
+      if (b2.y) {
+        if (b2.red) {
+          const float is = __ldg(b2.invstd + ch);
+          const float xh = (y2v[u] - __ldg(b2.mean + ch)) * is;
+          const float mg = (float)(b2.red[ch] * inv_n), mgx = (float)(b2.red[c + ch] * inv_n);
+          r2[u] = __ldg(b2.gamma + ch) * is * (gg - mg - xh * mgx);
+        } else {
+          r2[u] = gg * __ldg(b2.scale + ch);
+        }
+      }
+    }
+    if constexpr (V == 4) {
+      *reinterpret_cast<float4*>(b1.grad_y + idx) = make_float4(r1[0], r1[1], r1[2], r1[3]);
+      if (b2.y) *reinterpret_cast<float4*>(b2.grad_y + idx) = make_float4(r2[0], r2[1], r2[2], r2[3]);
+    } else {
+      b1.grad_y[idx] = r1[0];
+      if (b2.y) b2.grad_y[idx] = r2[0];
+    }
+  }
+}
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+static CatRows make_cat(const float* a1, int64_t ld1, int c1, const float* a2, int64_t ld2, int c2) {
+  CatRows A{a1, ld1, c1, a2, ld2, c2, false};
+  bool v = aligned16(a1) && (ld1 % 4 == 0) && (c1 % 4 == 0);
+  if (c2 > 0) v = v && aligned16(a2) && (ld2 % 4 == 0) && (c2 % 4 == 0);
+  A.vec = v;
+  return A;
+}
+
+static int elementwise_grid(int64_t work_items) {
+  int64_t blocks = ceil_div(work_items, 256);
+  const int64_t cap = (int64_t)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  return (int)(blocks < 1 ? 1 : blocks);
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_linear_fwd(const float* a1, int64_t ld1, int32_t c1, const float* a2, int64_t ld2, int32_t c2,
+                               const float* w, const float* bias, float* y, int64_t n, int32_t cout,
+                               double* colstats, void* stream) {
+  B200_REQUIRE(a1 && w && y, B200_E_INVALID, "b200_linear_fwd: null pointer");
+  B200_REQUIRE(c1 > 0 && c2 >= 0 && cout > 0 && (c2 == 0 || a2), B200_E_INVALID, "b200_linear_fwd: bad sizes");
+  B200_REQUIRE(ld1 >= c1 && (c2 == 0 || ld2 >= c2), B200_E_INVALID, "b200_linear_fwd: row stride < width");
+  if (n <= 0) return B200_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const CatRows A = make_cat(a1, ld1, c1, a2, ld2, c2);
+  const bool wvec = aligned16(w) && ((c1 + c2) % 4 == 0);
+  if (cout <= 32) {
+    dim3 grid((unsigned)ceil_div(n, 128), (unsigned)ceil_div(cout, 32));
+    linear_fwd_kernel<128, 32><<<grid, GEMM_THREADS, 0, st>>>(A, w, wvec, bias, y, n, cout, colstats);
+  } else {
+    dim3 grid((unsigned)ceil_div(n, 64), (unsigned)ceil_div(cout, 64));
+    linear_fwd_kernel<64, 64><<<grid, GEMM_THREADS, 0, st>>>(A, w, wvec, bias, y, n, cout, colstats);
+  }
+  B200_CHECK_LAUNCH("linear_fwd_kernel");
+  return B200_OK;
+}
+
+extern "C" int b200_linear_bwd_input(const float* grad_y, const float* w, float* ga1, int64_t ldg1, int32_t c1,
+                                     float* ga2, int64_t ldg2, int32_t c2, int64_t n, int32_t cout, void* stream) {
+  B200_REQUIRE(grad_y && w, B200_E_INVALID, "b200_linear_bwd_input: null pointer");
+  B200_REQUIRE(c1 > 0 && c2 >= 0 && cout > 0, B200_E_INVALID, "b200_linear_bwd_input: bad sizes");
+  if (n <= 0 || (!ga1 && !ga2)) return B200_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int ktot = c1 + c2;
+  const bool gvec = aligned16(grad_y) && (cout % 4 == 0);
+  const bool wvec = aligned16(w) && (ktot % 4 == 0);
+  if (ktot <= 32) {
+    dim3 grid((unsigned)ceil_div(n, 128), (unsigned)ceil_div(ktot, 32));
+    linear_bwd_input_kernel<128, 32><<<grid, GEMM_THREADS, 0, st>>>(grad_y, gvec, w, wvec, ga1, ldg1, c1, ga2, ldg2, c2, n, cout);
+  } else {
+    dim3 grid((unsigned)ceil_div(n, 64), (unsigned)ceil_div(ktot, 64));
+    linear_bwd_input_kernel<64, 64><<<grid, GEMM_THREADS, 0, st>>>(grad_y, gvec, w, wvec, ga1, ldg1, c1, ga2, ldg2, c2, n, cout);
+  }
+  B200_CHECK_LAUNCH("linear_bwd_input_kernel");
+  return B200_OK;
+}
+
+extern "C" int b200_linear_bwd_weight(const float* grad_y, const float* a1, int64_t ld1, int32_t c1, const float* a2,
+                                      int64_t ld2, int32_t c2, float* grad_w, float* grad_bias, int64_t n,
+                                      int32_t cout, void* stream) {
+  B200_REQUIRE(grad_y && a1 && grad_w, B200_E_INVALID, "b200_linear_bwd_weight: null pointer");
+  B200_REQUIRE(c1 > 0 && c2 >= 0 && cout > 0 && (c2 == 0 || a2), B200_E_INVALID, "b200_linear_bwd_weight: bad sizes");
+  if (n <= 0) return B200_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const CatRows A = make_cat(a1, ld1, c1, a2, ld2, c2);
+  const bool gvec = aligned16(grad_y) && (cout % 4 == 0);
+  const int ncols = c1 + c2 + (grad_bias ? 1 : 0);
+  const int64_t tiles = ceil_div(cout, 64) * ceil_div(ncols, 64);
+  int64_t splits = ceil_div((int64_t)num_sms() * 4, tiles);
+  const int64_t max_splits = ceil_div(n, 128);
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  if (splits > 65535) splits = 65535;
+  int64_t rows_per_split = ceil_div(n, splits);
+  rows_per_split = ceil_div(rows_per_split, GEMM_BK) * GEMM_BK;
+  splits = ceil_div(n, rows_per_split);
+  dim3 grid((unsigned)ceil_div(cout, 64), (unsigned)ceil_div(ncols, 64), (unsigned)splits);
+  linear_bwd_weight_kernel<64, 64><<<grid, GEMM_THREADS, 0, st>>>(grad_y, gvec, A, grad_w, grad_bias, n, cout, rows_per_split);
+  B200_CHECK_LAUNCH("linear_bwd_weight_kernel");
+  return B200_OK;
+}
+
+extern "C" int b200_bn_finalize(const double* colstats, int64_t count, const float* gamma, const float* beta,
+                                float* running_mean, float* running_var, float momentum, float eps, float* scale,
+                                float* shift, float* mean, float* invstd, int32_t c, void* stream) {
+  B200_REQUIRE(gamma && beta && scale && shift && c > 0, B200_E_INVALID, "b200_bn_finalize: null pointer / c <= 0");
+  B200_REQUIRE(colstats || (running_mean && running_var), B200_E_INVALID,
+               "b200_bn_finalize: eval mode needs running statistics");
+  B200_REQUIRE(!colstats || count > 0, B200_E_INVALID, "b200_bn_finalize: count must be positive");
+  B200_REQUIRE((running_mean == nullptr) == (running_var == nullptr), B200_E_INVALID,
+               "b200_bn_finalize: running_mean / running_var must come together");
+  bn_finalize_kernel<<<(unsigned)ceil_div(c, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      colstats, count, gamma, beta, running_mean, running_var, momentum, eps, scale, shift, mean, invstd, c);
+  B200_CHECK_LAUNCH("bn_finalize_kernel");
+  return B200_OK;
+}
+
+extern "C" int b200_affine_act_fwd(const float* y1, const float* scale1, const float* shift1, const float* y2,
+                                   const float* scale2, const float* shift2, float slope, float* out, int64_t n,
+                                   int32_t c, void* stream) {
+  B200_REQUIRE(y1 && scale1 && shift1 && out && c > 0, B200_E_INVALID, "b200_affine_act_fwd: null pointer");
+  B200_REQUIRE(!y2 || (scale2 && shift2), B200_E_INVALID, "b200_affine_act_fwd: second branch incomplete");
+  if (n <= 0) return B200_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t total = n * c;
+  const bool vec = (c % 4 == 0) && aligned16(y1) && aligned16(out) && (!y2 || aligned16(y2));
+  if (vec)
+    affine_act_fwd_kernel<4><<<elementwise_grid(total / 4), 256, 0, st>>>(y1, scale1, shift1, y2, scale2, shift2, slope, out, total, c);
+  else
+    affine_act_fwd_kernel<1><<<elementwise_grid(total), 256, 0, st>>>(y1, scale1, shift1, y2, scale2, shift2, slope, out, total, c);
+  B200_CHECK_LAUNCH("affine_act_fwd_kernel");
+  return B200_OK;
+}
+
+extern "C" int b200_affine_act_bwd_reduce(const float* grad_out, const float* out, float slope, const float* y1,
+                                          const float* mean1, const float* invstd1, double* red1, const float* y2,
+                                          const float* mean2, const float* invstd2, double* red2, int64_t n,
+                                          int32_t c, void* stream) {
+  B200_REQUIRE(grad_out && y1 && mean1 && invstd1 && red1 && c > 0, B200_E_INVALID, "b200_affine_act_bwd_reduce: null pointer");
+  B200_REQUIRE(slope == 1.f || out, B200_E_INVALID, "b200_affine_act_bwd_reduce: activation needs `out`");
+  B200_REQUIRE(!y2 || (mean2 && invstd2 && red2), B200_E_INVALID, "b200_affine_act_bwd_reduce: second branch incomplete");
+  if (n <= 0) return B200_OK;
+  int lanes = 1;
+  while (lanes < c && lanes < RED_THREADS) lanes <<= 1;
+  const int rstep = RED_THREADS / lanes;
+  int64_t blocks = ceil_div(n, (int64_t)rstep * 8);
+  const int64_t cap = (int64_t)num_sms() * 4;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  affine_act_bwd_reduce_kernel<<<(unsigned)blocks, RED_THREADS, 4 * lanes * sizeof(double), static_cast<cudaStream_t>(stream)>>>(
+      grad_out, out, slope, y1, mean1, invstd1, red1, y2, mean2, invstd2, red2, n, c, lanes);
+  B200_CHECK_LAUNCH("affine_act_bwd_reduce_kernel");
+  return B200_OK;
+}
+
+extern "C" int b200_affine_act_bwd_apply(const float* grad_out, const float* out, float slope, const float* y1,
+                                         const float* gamma1, const float* mean1, const float* invstd1,
+                                         const double* red1, const float* scale1, float* grad_y1, float* grad_gamma1,
+                                         float* grad_beta1, const float* y2, const float* gamma2, const float* mean2,
+                                         const float* invstd2, const double* red2, const float* scale2,
+                                         float* grad_y2, float* grad_gamma2, float* grad_beta2, int64_t n, int32_t c,
+                                         void* stream) {
+  B200_REQUIRE(grad_out && grad_y1 && c > 0, B200_E_INVALID, "b200_affine_act_bwd_apply: null pointer");
+  B200_REQUIRE(slope == 1.f || out, B200_E_INVALID, "b200_affine_act_bwd_apply: activation needs `out`");
+  B200_REQUIRE(red1 ? (y1 && gamma1 && mean1 && invstd1) : (scale1 != nullptr), B200_E_INVALID,
+               "b200_affine_act_bwd_apply: branch 1 incomplete");
+  B200_REQUIRE(!y2 || (grad_y2 && (red2 ? (gamma2 && mean2 && invstd2) : (scale2 != nullptr))), B200_E_INVALID,
+               "b200_affine_act_bwd_apply: branch 2 incomplete");
+  B200_REQUIRE((grad_gamma1 == nullptr) == (grad_beta1 == nullptr) && (grad_gamma2 == nullptr) == (grad_beta2 == nullptr),
+               B200_E_INVALID, "b200_affine_act_bwd_apply: grad_gamma / grad_beta must come together");
+  if (n <= 0) return B200_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  BnBranch b1{y1, gamma1, mean1, invstd1, red1, scale1, grad_y1, grad_gamma1, grad_beta1};
+  BnBranch b2{y2, gamma2, mean2, invstd2, red2, scale2, grad_y2, grad_gamma2, grad_beta2};
+  const int64_t total = n * c;
+  bool vec = (c % 4 == 0) && aligned16(grad_out) && aligned16(grad_y1) && (!out || aligned16(out)) &&
+             (!y1 || aligned16(y1)) && (!y2 || (aligned16(y2) && aligned16(grad_y2)));
+  if (vec)
+    affine_act_bwd_apply_kernel<4><<<elementwise_grid(total / 4), 256, 0, st>>>(grad_out, out, slope, b1, b2, n, c);
+  else
+    affine_act_bwd_apply_kernel<1><<<elementwise_grid(total), 256, 0, st>>>(grad_out, out, slope, b1, b2, n, c);
+  B200_CHECK_LAUNCH("affine_act_bwd_apply_kernel");
+  return B200_OK;
+}

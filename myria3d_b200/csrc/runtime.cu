@@ -1,0 +1,61 @@
+// Error convention, launch counter and device check of the C ABI (include/b200randla.h).
+#include <atomic>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace b200 {
+
+static thread_local char g_err[512] = {0};
+static std::atomic<int64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+  cudaGetLastError();  // clear the sticky-less error so later calls are not poisoned
+  return B200_E_CUDA;
+}
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int num_sms() {
+  static thread_local int cached_dev = -1;
+  static thread_local int cached_sms = 148;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (dev != cached_dev) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) cached_sms = v;
+    cached_dev = dev;
+  }
+  return cached_sms;
+}
+
+}  // namespace b200
+
+extern "C" {
+
+int b200_abi_version(void) { return B200_ABI_VERSION; }
+
+const char* b200_last_error(void) { return b200::g_err; }
+
+int64_t b200_launch_count(void) { return b200::g_launches.load(std::memory_order_relaxed); }
+
+int b200_check_device(void) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return b200::cuda_fail(e, "cudaGetDevice");
+  int major = 0, minor = 0;
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+  B200_REQUIRE(major == 10, B200_E_UNSUPPORTED, "libb200randla needs an sm_100 device, found sm_%d%d", major, minor);
+  return B200_OK;
+}
+
+}  // extern "C"

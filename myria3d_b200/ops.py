@@ -1,0 +1,345 @@
+"""Host-side operators of the B200 RandLA-Net hot path: thin wrappers + ``torch.autograd.Function``s
+over the C ABI of ``libb200randla.so``.  PyTorch only owns device memory, streams and the autograd
+graph; every computation on ``[N, .]`` / ``[E, .]`` data is a kernel of the library.
+
+Each operator cites the reference call it stands for (paths relative to the myria3d repository).
+"""
+from __future__ import annotations
+
+from ctypes import c_void_p
+from typing import Optional, Sequence, Tuple
+
+import torch
+from torch import Tensor
+from torch.autograd.function import once_differentiable
+
+from . import _lib
+
+LRELU_SLOPE = 0.2  # myria3d/models/modules/pyg_randla_net.py:92
+BN_MOMENTUM = 0.01  # pyg_randla_net.py:94
+BN_EPS = 1e-6  # pyg_randla_net.py:94
+
+
+def _p(t: Optional[Tensor]) -> Optional[c_void_p]:
+    return None if t is None else c_void_p(t.data_ptr())
+
+
+def _stream() -> c_void_p:
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _call(name: str, *args) -> None:
+    """Enqueue one library entry point on the current stream (optionally timed by ``_lib.PROFILER``)."""
+    lib = _lib.load()
+    prof = _lib.PROFILER
+    if prof is None:
+        _lib.check(getattr(lib, name)(*args), name)
+        return
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    rc = getattr(lib, name)(*args)
+    end.record()
+    _lib.check(rc, name)
+    prof.add(name, args, start, end)
+
+
+def _need_cuda(*ts: Optional[Tensor]) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError(
+                "myria3d_b200 operators run on a B200 only (got a CPU tensor); there is no CPU fallback"
+            )
+
+
+def _f32c(t: Tensor) -> Tensor:
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def table_width(k: int) -> int:
+    """Neighbour-table width used by the fused LFA kernels for ``k`` neighbours."""
+    if k <= 16:
+        return 16
+    if k <= 32:
+        return 32
+    raise ValueError(f"num_neighbors={k} > 32 is not supported by the fused LFA kernels")
+
+
+# ------------------------------------------------------------------------------------------- kNN
+def knn(pos_x: Tensor, ptr_x: Tensor, pos_y: Tensor, ptr_y: Tensor, k: int, max_queries_per_cloud: int,
+        kt: Optional[int] = None, want_dist: bool = True) -> Tuple[Tensor, Optional[Tensor]]:
+    """k nearest ``pos_x`` points of the same cloud for every ``pos_y`` point.
+
+    Stands for torch_cluster ``knn`` behind ``knn_graph`` (pyg_randla_net.py:180) and
+    ``knn_interpolate`` (pyg_randla_net.py:250, models/model.py:90).  Returns ``nbr`` int32
+    ``[ny, kt]`` (-1 padded) and ``dist2`` fp32 ``[ny, kt]`` (inf padded).
+    """
+    _need_cuda(pos_x, ptr_x, pos_y, ptr_y)
+    kt = k if kt is None else kt
+    pos_x, pos_y = _f32c(pos_x), _f32c(pos_y)
+    ptr_x = ptr_x.to(torch.int64).contiguous()
+    ptr_y = ptr_y.to(torch.int64).contiguous()
+    ny = pos_y.shape[0]
+    nbr = torch.empty((ny, kt), dtype=torch.int32, device=pos_y.device)
+    dist2 = torch.empty((ny, kt), dtype=torch.float32, device=pos_y.device) if want_dist else None
+    _call("b200_knn", _p(pos_x), _p(ptr_x), pos_x.shape[0], _p(pos_y), _p(ptr_y), ny,
+                              ptr_x.numel() - 1, int(max_queries_per_cloud), k, kt, _p(nbr), _p(dist2), _stream())
+    return nbr, dist2
+
+
+def edge_moments(pos: Tensor, nbr: Tensor) -> Tensor:
+    """fp64 ``[57]``: edge count, sum q, sum q q^T for q = (p_i, p_j, |p_j - p_i|) over all edges."""
+    _need_cuda(pos, nbr)
+    out = torch.zeros(57, dtype=torch.float64, device=pos.device)
+    _call("b200_edge_moments", _p(pos), _p(nbr), pos.shape[0], nbr.shape[1], _p(out), _stream())
+    return out
+
+
+# ------------------------------------------------------------------ LocSE + attentive pooling
+class _LFAFunction(torch.autograd.Function):
+    """propagate()+message() of LocalFeatureAggregation (pyg_randla_net.py:121-152), fused."""
+
+    @staticmethod
+    def forward(ctx, x, pos, nbr, enc_w, enc_b, att_w):
+        x, enc_w, enc_b, att_w = _f32c(x), _f32c(enc_w), _f32c(enc_b), _f32c(att_w)
+        att_wt = att_w.t().contiguous()
+        n, h = x.shape
+        c = 2 * h
+        out = torch.empty((n, c), dtype=torch.float32, device=x.device)
+        _call("b200_lfa_fwd", _p(x), _p(pos), _p(nbr), _p(enc_w), _p(enc_b), _p(att_wt), _p(out),
+                                      n, c, nbr.shape[1], _stream())
+        ctx.save_for_backward(x, pos, nbr, enc_w, enc_b, att_wt, att_w)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_out):
+        x, pos, nbr, enc_w, enc_b, att_wt, att_w = ctx.saved_tensors
+        grad_out = _f32c(grad_out)
+        n, h = x.shape
+        c = 2 * h
+        gx = torch.zeros_like(x)
+        gew = torch.zeros_like(enc_w)
+        geb = torch.zeros_like(enc_b)
+        gaw = torch.zeros_like(att_w)
+        _call("b200_lfa_bwd", _p(x), _p(pos), _p(nbr), _p(enc_w), _p(enc_b), _p(att_wt), _p(att_w),
+                                      _p(grad_out), _p(gx), _p(gew), _p(geb), _p(gaw), n, c, nbr.shape[1], _stream())
+        return gx, None, None, gew, geb, gaw
+
+
+def lfa_attentive_pool(x: Tensor, pos: Tensor, nbr: Tensor, enc_w: Tensor, enc_b: Tensor, att_w: Tensor) -> Tensor:
+    """``sum_j softmax_j(W_att f_ij) * f_ij`` with ``f_ij = [x_j ; lrelu(enc_w q_ij + enc_b)]``.
+
+    ``enc_w`` ``[c/2, 7]`` / ``enc_b`` act on ``q = (p_i, p_j, |p_j-p_i|)`` and already contain the
+    encoder BatchNorm (see :func:`myria3d_b200.randla_net.fold_encoder`)."""
+    _need_cuda(x, pos, nbr, enc_w, enc_b, att_w)
+    if nbr.dtype != torch.int32 or nbr.shape[1] not in (16, 32):
+        raise ValueError("nbr must be an int32 [N, 16|32] neighbour table")
+    if x.shape[1] * 2 != att_w.shape[0] or att_w.shape[0] != att_w.shape[1]:
+        raise ValueError(f"shape mismatch: x {tuple(x.shape)}, att_w {tuple(att_w.shape)}")
+    return _LFAFunction.apply(x, _f32c(pos), nbr.contiguous(), enc_w, enc_b, att_w)
+
+
+# ------------------------------------------------------------------------- index / scatter ops
+class _GatherRows(torch.autograd.Function):
+    """``tensor[idx_decim]`` of decimate() (pyg_randla_net.py:237) and its backward."""
+
+    @staticmethod
+    def forward(ctx, x, idx):
+        x = _f32c(x)
+        out = torch.empty((idx.numel(), x.shape[1]), dtype=torch.float32, device=x.device)
+        _call("b200_gather_rows", _p(x), _p(idx), _p(out), idx.numel(), x.shape[1], _stream())
+        ctx.save_for_backward(idx)
+        ctx.n_src = x.shape[0]
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_out):
+        (idx,) = ctx.saved_tensors
+        grad_out = _f32c(grad_out)
+        gx = torch.zeros((ctx.n_src, grad_out.shape[1]), dtype=torch.float32, device=grad_out.device)
+        _call("b200_scatter_rows_add", _p(grad_out), _p(idx), _p(gx), idx.numel(), grad_out.shape[1], _stream())
+        return gx, None
+
+
+def gather_rows(x: Tensor, idx: Tensor) -> Tensor:
+    _need_cuda(x, idx)
+    if idx.dtype != torch.int64:
+        idx = idx.to(torch.int64)
+    return _GatherRows.apply(x, idx.contiguous())
+
+
+class _KnnInterpolate(torch.autograd.Function):
+    """Weighting tail of ``knn_interpolate`` (pyg_randla_net.py:250; models/model.py:90-98)."""
+
+    @staticmethod
+    def forward(ctx, x, nbr, dist2, k):
+        x = _f32c(x)
+        ny, c = nbr.shape[0], x.shape[1]
+        out = torch.empty((ny, c), dtype=torch.float32, device=x.device)
+        _call("b200_knn_interp_fwd", _p(x), _p(nbr), _p(dist2), _p(out), ny, c, k, nbr.shape[1], c, _stream())
+        ctx.save_for_backward(nbr, dist2)
+        ctx.k, ctx.nx = k, x.shape[0]
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_out):
+        nbr, dist2 = ctx.saved_tensors
+        grad_out = _f32c(grad_out)
+        c = grad_out.shape[1]
+        gx = torch.zeros((ctx.nx, c), dtype=torch.float32, device=grad_out.device)
+        _call("b200_knn_interp_bwd", _p(grad_out), c, _p(nbr), _p(dist2), _p(gx), nbr.shape[0], c, ctx.k,
+                                             nbr.shape[1], _stream())
+        return gx, None, None, None
+
+
+def knn_interpolate_from_table(x: Tensor, nbr: Tensor, dist2: Tensor, k: int) -> Tensor:
+    _need_cuda(x, nbr, dist2)
+    return _KnnInterpolate.apply(x, nbr, dist2, k)
+
+
+# ---------------------------------------------------------------------------- per-point layers
+class _Linear(torch.autograd.Function):
+    """``[a1 | a2] @ W^T + b`` (torch.nn.Linear / PyG Linear inside SharedMLP, pyg_randla_net.py:42,53,97-109;
+    the concatenation is FPModule's ``torch.cat([x, x_skip], dim=1)``, :251).  Optionally returns the
+    per-column (sum, sum of squares) in fp64 for the BatchNorm that follows."""
+
+    @staticmethod
+    def forward(ctx, a1, a2, w, b, want_stats):
+        a1, w = _f32c(a1), _f32c(w)
+        a2 = _f32c(a2) if a2 is not None else None
+        n, c1 = a1.shape
+        c2 = a2.shape[1] if a2 is not None else 0
+        cout = w.shape[0]
+        if w.shape[1] != c1 + c2:
+            raise RuntimeError(f"mat1 and mat2 shapes cannot be multiplied ({n}x{c1 + c2} and {w.shape[1]}x{cout})")
+        y = torch.empty((n, cout), dtype=torch.float32, device=a1.device)
+        stats = torch.zeros(2 * cout, dtype=torch.float64, device=a1.device) if want_stats else None
+        _call("b200_linear_fwd", _p(a1), c1, c1, _p(a2), c2, c2, _p(w), _p(b), _p(y), n, cout, _p(stats), _stream())
+        ctx.save_for_backward(a1, a2, w)
+        ctx.has_bias = b is not None
+        if want_stats:
+            ctx.mark_non_differentiable(stats)
+            return y, stats
+        return y, None
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_y, _grad_stats):
+        a1, a2, w = ctx.saved_tensors
+        grad_y = _f32c(grad_y)
+        n, c1 = a1.shape
+        c2 = a2.shape[1] if a2 is not None else 0
+        cout = w.shape[0]
+        lib = _lib.load()
+        ga1 = torch.empty_like(a1) if ctx.needs_input_grad[0] else None
+        ga2 = torch.empty_like(a2) if (a2 is not None and ctx.needs_input_grad[1]) else None
+        if ga1 is not None or ga2 is not None:
+            _call("b200_linear_bwd_input", _p(grad_y), _p(w), _p(ga1), c1, c1, _p(ga2), c2, c2, n, cout, _stream())
+        gw = gb = None
+        if ctx.needs_input_grad[2] or (ctx.has_bias and ctx.needs_input_grad[3]):
+            gw = torch.zeros_like(w)
+            gb = torch.zeros(cout, dtype=torch.float32, device=w.device) if ctx.has_bias else None
+            _call("b200_linear_bwd_weight", _p(grad_y), _p(a1), c1, c1, _p(a2), c2, c2, _p(gw), _p(gb), n, cout, _stream())
+        return ga1, ga2, gw, gb, None
+
+
+def linear(a1: Tensor, w: Tensor, b: Optional[Tensor] = None, a2: Optional[Tensor] = None, want_stats: bool = False):
+    _need_cuda(a1, a2, w, b)
+    y, stats = _Linear.apply(a1, a2, w, b, want_stats)
+    return (y, stats) if want_stats else y
+
+
+class _BNAct(torch.autograd.Function):
+    """``act(BN(y1) [+ BN(y2)])``: BatchNorm1d(momentum .01, eps 1e-6) + LeakyReLU(.2) of SharedMLP
+    (pyg_randla_net.py:94-109) and the residual tail ``lrelu(mlp2(x) + shortcut(x))`` (:186-187).
+
+    ``stats*`` are the fp64 column sums from :class:`_Linear` (training) or ``None`` (eval: running
+    statistics).  Running buffers are updated in place like ``torch.nn.BatchNorm1d``.
+    """
+
+    @staticmethod
+    def forward(ctx, y1, stats1, g1, b1, rm1, rv1, y2, stats2, g2, b2, rm2, rv2, slope, momentum, eps):
+        lib = _lib.load()
+        n, c = y1.shape
+        dev = y1.device
+        training = stats1 is not None
+
+        def finalize(stats, g, b, rm, rv):
+            buf = torch.empty((4, c), dtype=torch.float32, device=dev)  # scale, shift, mean, invstd
+            _call("b200_bn_finalize", _p(stats), n, _p(g), _p(b), _p(rm), _p(rv), momentum, eps,
+                                      _p(buf[0]), _p(buf[1]), _p(buf[2]), _p(buf[3]), c, _stream())
+            return buf
+
+        g1, b1 = _f32c(g1), _f32c(b1)
+        aff1 = finalize(stats1, g1, b1, rm1, rv1)
+        aff2 = None
+        if y2 is not None:
+            g2, b2 = _f32c(g2), _f32c(b2)
+            aff2 = finalize(stats2, g2, b2, rm2, rv2)
+        out = torch.empty_like(y1)
+        _call("b200_affine_act_fwd", _p(y1), _p(aff1[0]), _p(aff1[1]), _p(y2),
+                                     _p(aff2[0]) if aff2 is not None else None,
+                                     _p(aff2[1]) if aff2 is not None else None, slope, _p(out), n, c, _stream())
+        ctx.save_for_backward(y1, g1, aff1, y2, g2 if y2 is not None else None, aff2, out)
+        ctx.slope, ctx.training = slope, training
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_out):
+        y1, g1, aff1, y2, g2, aff2, out = ctx.saved_tensors
+        grad_out = _f32c(grad_out)
+        lib = _lib.load()
+        n, c = y1.shape
+        dev = y1.device
+        red1 = torch.zeros(2 * c, dtype=torch.float64, device=dev)
+        red2 = torch.zeros(2 * c, dtype=torch.float64, device=dev) if y2 is not None else None
+        _call("b200_affine_act_bwd_reduce", _p(grad_out), _p(out), ctx.slope, _p(y1), _p(aff1[2]), _p(aff1[3]), _p(red1),
+                                            _p(y2), _p(aff2[2]) if y2 is not None else None,
+                                            _p(aff2[3]) if y2 is not None else None, _p(red2), n, c, _stream())
+        gy1 = torch.empty_like(y1)
+        gy2 = torch.empty_like(y2) if y2 is not None else None
+        tr = ctx.training
+        _call("b200_affine_act_bwd_apply", 
+            _p(grad_out), _p(out), ctx.slope,
+            _p(y1), _p(g1), _p(aff1[2]), _p(aff1[3]), _p(red1) if tr else None, _p(aff1[0]), _p(gy1), None, None,
+            _p(y2), _p(g2), _p(aff2[2]) if y2 is not None else None, _p(aff2[3]) if y2 is not None else None,
+            _p(red2) if (tr and y2 is not None) else None, _p(aff2[0]) if y2 is not None else None, _p(gy2), None, None,
+            n, c, _stream())
+        gg1, gb1 = red1[c:].float(), red1[:c].float()
+        gg2 = gb2 = None
+        if y2 is not None:
+            gg2, gb2 = red2[c:].float(), red2[:c].float()
+        return (gy1, None, gg1, gb1, None, None, gy2, None, gg2, gb2, None, None, None, None, None)
+
+
+def bn_act(y: Tensor, stats: Optional[Tensor], bn: torch.nn.BatchNorm1d, slope: float,
+           y2: Optional[Tensor] = None, stats2: Optional[Tensor] = None, bn2: Optional[torch.nn.BatchNorm1d] = None) -> Tensor:
+    """BatchNorm (+ second normalised branch) + LeakyReLU(slope) (slope=1.0: no activation)."""
+    _need_cuda(y, y2)
+    training = stats is not None
+    if training and y.shape[0] <= 1:
+        # same failure as torch.nn.BatchNorm1d in training mode
+        raise ValueError(f"Expected more than 1 value per channel when training, got input size {tuple(y.shape)}")
+
+    def buffers(m):
+        if m.running_mean is None:
+            raise RuntimeError("BatchNorm without running statistics is not supported")
+        return m.running_mean, m.running_var
+
+    rm1, rv1 = buffers(bn)
+    args2 = (None, None, None, None, None, None)
+    if y2 is not None:
+        rm2, rv2 = buffers(bn2)
+        args2 = (y2, stats2, bn2.weight, bn2.bias, rm2, rv2)
+    out = _BNAct.apply(y, stats, bn.weight, bn.bias, rm1, rv1, *args2, float(slope), float(bn.momentum), float(bn.eps))
+    if training:
+        with torch.no_grad():
+            bn.num_batches_tracked += 1
+            if bn2 is not None:
+                bn2.num_batches_tracked += 1
+    return out

@@ -1,0 +1,300 @@
+"""Per-kernel parity tests: libb200randla (through the C ABI / ops layer) vs the CPU oracle.
+
+Integer / index outputs are compared bit-exactly; floating outputs with the tolerance written at
+each assertion.
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import randla_oracle as O
+from tests.helpers import assert_close, ptr_of, rand_cloud, rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+# ------------------------------------------------------------------------------------------ kNN
+@pytest.mark.parametrize("sizes,k", [([700, 50, 1, 3, 1301], 16), ([5, 2100], 16), ([12, 3000, 7], 32), ([40, 900], 10),
+                                     ([2500], 1)])
+def test_knn_self_bit_exact(lib, sizes, k):
+    from myria3d_b200 import ops
+
+    _, pos, _, ptr = rand_cloud(sizes, seed=1)
+    nbr_ref, deg_ref = O.knn_bruteforce(pos, ptr.tolist(), pos, ptr.tolist(), k)
+    d2_ref = torch.full(nbr_ref.shape, float("inf"))
+    m = nbr_ref >= 0
+    q = torch.arange(pos.shape[0]).unsqueeze(1).expand_as(nbr_ref)
+    d2_ref[m] = O._canonical_d2(pos[q[m]], pos[nbr_ref[m]])
+    kt = ops.table_width(k) if k in (16, 32) else k
+    nbr, d2 = ops.knn(pos.to(DEV), ptr.to(DEV), pos.to(DEV), ptr.to(DEV), k, max(sizes), kt=kt)
+    assert nbr.dtype == torch.int32 and nbr.shape == (sum(sizes), kt)
+    assert torch.equal(nbr.cpu()[:, :k].long(), nbr_ref), "kNN indices differ from the oracle"
+    assert torch.equal(d2.cpu()[:, :k], d2_ref), "kNN squared distances differ bitwise"
+    assert (nbr.cpu()[:, k:] == -1).all()
+    # self is the nearest neighbour
+    assert torch.equal(nbr.cpu()[:, 0].long(), torch.arange(sum(sizes)))
+
+
+@pytest.mark.parametrize("k", [1, 10])
+def test_knn_query_bit_exact(lib, k):
+    from myria3d_b200 import ops
+
+    sx, sy = [300, 9, 1, 1025], [1200, 36, 5, 4100]
+    g = torch.Generator().manual_seed(7)
+    pos_x = torch.rand(sum(sx), 3, generator=g)
+    pos_y = torch.rand(sum(sy), 3, generator=g)
+    nbr_ref, _ = O.knn_bruteforce(pos_x, ptr_of(sx), pos_y, ptr_of(sy), k)
+    nbr, d2 = ops.knn(pos_x.to(DEV), torch.tensor(ptr_of(sx), device=DEV), pos_y.to(DEV),
+                      torch.tensor(ptr_of(sy), device=DEV), k, max(sy))
+    assert torch.equal(nbr.cpu().long(), nbr_ref)
+    # kd-tree oracle agrees with the brute-force oracle (pins the baseline's kNN too)
+    nbr_kd, _ = O.knn_kdtree(pos_x, ptr_of(sx), pos_y, ptr_of(sy), k)
+    assert torch.equal(nbr_kd, nbr_ref)
+
+
+def test_knn_large_property(lib):
+    """BASELINE-size cloud (12 800 pts, K=16): size-independent properties + kd-tree oracle."""
+    from myria3d_b200 import ops
+
+    x, pos, y, batch, ptr = O.synthetic_batch([12800, 12800], seed=3)
+    nbr, d2 = ops.knn(pos.to(DEV), ptr.to(DEV), pos.to(DEV), ptr.to(DEV), 16, 12800, kt=16)
+    nbr, d2 = nbr.cpu().long(), d2.cpu()
+    assert torch.equal(nbr[:, 0], torch.arange(25600))  # self first (distance 0)
+    assert (d2[:, 1:] >= d2[:, :-1]).all()  # ascending
+    assert ((nbr[:12800] < 12800).all() and (nbr[12800:] >= 12800).all())  # never crosses clouds
+    assert (nbr.sort(dim=1).values[:, 1:] != nbr.sort(dim=1).values[:, :-1]).all()  # no duplicates
+    ref, _ = O.knn_kdtree(pos, ptr.tolist(), pos, ptr.tolist(), 16)
+    assert torch.equal(nbr, ref)
+
+
+# ---------------------------------------------------------------------------------- edge moments
+def test_edge_moments(lib):
+    from myria3d_b200 import ops
+
+    sizes = [333, 7, 1200]
+    _, pos, _, ptr = rand_cloud(sizes, seed=2)
+    nbr, _ = O.knn_bruteforce(pos, ptr.tolist(), pos, ptr.tolist(), 16)
+    m = nbr >= 0
+    i = torch.arange(pos.shape[0]).unsqueeze(1).expand_as(nbr)[m]
+    j = nbr[m]
+    d = pos[j] - pos[i]
+    dist = torch.sqrt((d * d).sum(1, keepdim=True))
+    q = torch.cat([pos[i], pos[j], dist], 1).double()
+    ref = torch.cat([torch.tensor([float(q.shape[0])], dtype=torch.float64), q.sum(0), (q.t() @ q).flatten()])
+    out = ops.edge_moments(pos.to(DEV), nbr.int().to(DEV)).cpu()
+    assert out[0].item() == q.shape[0]
+    assert_close(out, ref, atol=1e-9, rtol=1e-8, what="edge moments")
+
+
+# ------------------------------------------------------------------------- LFA forward / backward
+@pytest.mark.parametrize("c,k", [(8, 16), (16, 16), (32, 16), (64, 16), (128, 16), (256, 16), (16, 32), (64, 32), (256, 32)])
+@pytest.mark.parametrize("training", [True, False])
+def test_lfa_module_parity(lib, c, k, training):
+    """Product LocalFeatureAggregation (fused kernels + BN fold) vs the oracle module: output, input
+    gradient and every parameter gradient.  Tolerance 2e-4 relative (fp32, different summation order)."""
+    from myria3d_b200 import ops
+    from myria3d_b200.randla_net import LocalFeatureAggregation, _Level
+
+    sizes = [230, 9, 70] if k == 16 else [150, 20]
+    _, pos, _, ptr = rand_cloud(sizes, seed=c + k)
+    n = sum(sizes)
+    g = torch.Generator().manual_seed(c)
+    x = torch.randn(n, c // 2, generator=g)
+    go = torch.randn(n, c, generator=g)
+
+    ref = O.LocalFeatureAggregation(c)
+    # non-trivial BatchNorm state
+    for bn in (ref.mlp_encoder.norms[0].module, ref.mlp_post_attention.norms[0].module):
+        bn.weight.data.uniform_(0.5, 1.5, generator=g)
+        bn.bias.data.uniform_(-0.5, 0.5, generator=g)
+        bn.running_mean.uniform_(-0.3, 0.3, generator=g)
+        bn.running_var.uniform_(0.5, 1.5, generator=g)
+    ref.train(training)
+    mod = LocalFeatureAggregation(c)
+    mod.load_state_dict(ref.state_dict())
+    mod.to(DEV).train(training)
+
+    edge_index = O.knn_graph(pos, k, ptr.tolist(), method="brute")
+    xr = x.clone().requires_grad_(True)
+    out_ref = ref(edge_index, xr, pos)
+    out_ref.backward(go)
+
+    lvl = _Level(ptr.tolist(), torch.device(DEV))
+    nbr, _ = ops.knn(pos.to(DEV), lvl.ptr, pos.to(DEV), lvl.ptr, k, lvl.max_n, kt=ops.table_width(k), want_dist=False)
+    moments = ops.edge_moments(pos.to(DEV), nbr) if training else None
+    xg = x.to(DEV).requires_grad_(True)
+    out = mod(xg, pos.to(DEV), nbr, moments, lvl.num_edges(k))
+    out.backward(go.to(DEV))
+
+    assert_close(out, out_ref, atol=2e-4 * float(out_ref.abs().max()), what=f"LFA({c}) output")
+    assert rel_err(xg.grad, xr.grad) < 2e-4, f"grad_x rel err {rel_err(xg.grad, xr.grad)}"
+    ref_params = dict(ref.named_parameters())
+    for name, p in mod.named_parameters():
+        r = ref_params[name].grad
+        assert p.grad is not None, name
+        e = rel_err(p.grad, r)
+        scale = float(r.abs().max())
+        if training and name.endswith("lins.0.bias") and "attention.lins" not in name.replace("post_attention", ""):
+            # a Linear bias followed by train-mode BatchNorm has a mathematically ZERO gradient: the
+            # reference's value is fp32 round-off noise, the fused path returns (almost) exact zeros
+            wref = ref_params[name.replace("bias", "weight")].grad
+            assert float(p.grad.abs().max()) <= 1e-3 * float(wref.abs().max()) + 1e-6, f"{name}: not ~0"
+            continue
+        assert e < 5e-4 or float((p.grad.cpu() - r).abs().max()) < 1e-5 * max(1.0, scale), f"{name}: rel err {e}"
+    if training:
+        for name, b in mod.named_buffers():
+            assert_close(b, dict(ref.named_buffers())[name], atol=1e-5, rtol=1e-5, what=name)
+
+
+# ------------------------------------------------------------------------------ per-point layers
+def test_linear_stats_cancellation(lib):
+    """|mean| >> std: the fp64 statistics epilogue must still resolve the variance (2-row batches of
+    tiny clouds hit this in every deep level of the [50, 50] reference test)."""
+    from myria3d_b200 import ops
+
+    g = torch.Generator().manual_seed(0)
+    for n in (2, 300):
+        a = torch.randn(n, 16, generator=g) * 1e-3 + 3.0
+        w = torch.randn(8, 16, generator=g)
+        b = torch.randn(8, generator=g) + 50.0
+        yr = F.linear(a, w, b).double()
+        y, stats = ops.linear(a.to(DEV), w.to(DEV), b.to(DEV), want_stats=True)
+        mean = stats[:8] / n
+        var = stats[8:] / n - mean * mean
+        assert_close(y, yr, atol=2e-5, what="y")
+        ycpu = y.double().cpu()
+        assert_close(var, ycpu.var(0, unbiased=False), atol=0.0, rtol=1e-6, what=f"variance n={n}")
+
+
+@pytest.mark.parametrize("n,c1,c2,cout", [(1000, 9, 0, 32), (777, 32, 32, 32), (130, 512, 256, 256), (2048, 32, 0, 7),
+                                          (65, 64, 0, 64), (3, 4, 0, 8), (515, 128, 32, 32)])
+def test_linear_fwd_bwd(lib, n, c1, c2, cout):
+    from myria3d_b200 import ops
+
+    g = torch.Generator().manual_seed(n)
+    a1 = torch.randn(n, c1, generator=g)
+    a2 = torch.randn(n, c2, generator=g) if c2 else None
+    w = torch.randn(cout, c1 + c2, generator=g) / (c1 + c2) ** 0.5
+    b = torch.randn(cout, generator=g)
+    gy = torch.randn(n, cout, generator=g)
+    ar = [t.clone().requires_grad_(True) for t in (a1, w, b)] + ([a2.clone().requires_grad_(True)] if c2 else [])
+    inp = torch.cat([ar[0], ar[3]], 1) if c2 else ar[0]
+    yr = F.linear(inp, ar[1], ar[2])
+    yr.backward(gy)
+
+    ag = [t.to(DEV).requires_grad_(True) for t in (a1, w, b)] + ([a2.to(DEV).requires_grad_(True)] if c2 else [])
+    y, stats = ops.linear(ag[0], ag[1], ag[2], a2=ag[3] if c2 else None, want_stats=True)
+    y.backward(gy.to(DEV))
+    tol = 1e-5 * (c1 + c2) ** 0.5
+    assert_close(y, yr, atol=tol, rtol=1e-5, what="linear y")
+    assert_close(stats[:cout], yr.double().sum(0), atol=1e-3, rtol=1e-5, what="column sums")
+    assert_close(stats[cout:], (yr.double() ** 2).sum(0), atol=1e-3, rtol=1e-5, what="column sums of squares")
+    assert_close(ag[0].grad, ar[0].grad, atol=1e-5 * cout ** 0.5 * 3, rtol=1e-5, what="grad a1")
+    if c2:
+        assert_close(ag[3].grad, ar[3].grad, atol=1e-5 * cout ** 0.5 * 3, rtol=1e-5, what="grad a2")
+    assert rel_err(ag[1].grad, ar[1].grad) < 1e-5, "grad w"
+    assert rel_err(ag[2].grad, ar[2].grad) < 1e-5, "grad b"
+
+
+@pytest.mark.parametrize("n,c", [(1000, 32), (257, 512), (5000, 4), (2, 64), (300, 40)])
+@pytest.mark.parametrize("dual", [False, True])
+@pytest.mark.parametrize("training", [True, False])
+def test_bn_act(lib, n, c, dual, training):
+    from myria3d_b200 import ops
+
+    g = torch.Generator().manual_seed(n + c)
+    y1 = torch.randn(n, c, generator=g) * 2 + 0.7
+    y2 = torch.randn(n, c, generator=g) - 0.3
+    go = torch.randn(n, c, generator=g)
+
+    def make_bn():
+        bn = torch.nn.BatchNorm1d(c, eps=1e-6, momentum=0.01)
+        bn.weight.data.uniform_(0.5, 1.5, generator=g)
+        bn.bias.data.uniform_(-0.5, 0.5, generator=g)
+        bn.running_mean.uniform_(-0.3, 0.3, generator=g)
+        bn.running_var.uniform_(0.5, 1.5, generator=g)
+        return bn
+
+    import copy
+
+    bn1, bn2 = make_bn(), make_bn()
+    gb1, gb2 = copy.deepcopy(bn1).to(DEV), copy.deepcopy(bn2).to(DEV)
+    for m in (bn1, bn2, gb1, gb2):
+        m.train(training)
+    r1, r2 = y1.clone().requires_grad_(True), y2.clone().requires_grad_(True)
+    pre = bn1(r1) + (bn2(r2) if dual else 0)
+    out_ref = F.leaky_relu(pre, 0.2)
+    out_ref.backward(go)
+
+    d1, d2 = y1.to(DEV).requires_grad_(True), y2.to(DEV).requires_grad_(True)
+
+    def stats(t):
+        td = t.detach().double()
+        return torch.cat([td.sum(0), (td * td).sum(0)]) if training else None
+
+    out = ops.bn_act(d1, stats(d1), gb1, 0.2, y2=d2 if dual else None, stats2=stats(d2) if dual else None,
+                     bn2=gb2 if dual else None)
+    out.backward(go.to(DEV))
+    assert_close(out, out_ref, atol=2e-5, rtol=1e-5, what="bn_act out")
+    assert_close(d1.grad, r1.grad, atol=2e-5, rtol=1e-4, what="grad y1")
+    assert rel_err(gb1.weight.grad, bn1.weight.grad) < 1e-4
+    assert rel_err(gb1.bias.grad, bn1.bias.grad) < 1e-4
+    assert_close(gb1.running_mean, bn1.running_mean, atol=1e-6, rtol=1e-5, what="running_mean")
+    assert_close(gb1.running_var, bn1.running_var, atol=1e-6, rtol=1e-5, what="running_var")
+    assert int(gb1.num_batches_tracked) == int(bn1.num_batches_tracked)
+    if dual:
+        assert_close(d2.grad, r2.grad, atol=2e-5, rtol=1e-4, what="grad y2")
+        assert rel_err(gb2.weight.grad, bn2.weight.grad) < 1e-4
+        assert_close(gb2.running_var, bn2.running_var, atol=1e-6, rtol=1e-5, what="running_var 2")
+
+
+def test_bn_single_row_raises(lib):
+    from myria3d_b200 import ops
+
+    bn = torch.nn.BatchNorm1d(8).to(DEV)
+    y = torch.randn(1, 8, device=DEV)
+    with pytest.raises(ValueError):
+        ops.bn_act(y, torch.zeros(16, dtype=torch.float64, device=DEV), bn, 0.2)
+
+
+# ------------------------------------------------------------------------------- index / scatter
+@pytest.mark.parametrize("c", [3, 32, 7, 512])
+def test_gather_rows_bit_exact(lib, c):
+    from myria3d_b200 import ops
+
+    g = torch.Generator().manual_seed(c)
+    x = torch.randn(1000, c, generator=g)
+    idx = torch.randperm(1000, generator=g)[:333]
+    xg = x.to(DEV).requires_grad_(True)
+    out = ops.gather_rows(xg, idx.to(DEV))
+    assert torch.equal(out.cpu(), x[idx])
+    go = torch.randn(333, c, generator=g)
+    out.backward(go.to(DEV))
+    ref = torch.zeros_like(x).index_add(0, idx, go)
+    assert torch.equal(xg.grad.cpu(), ref)
+
+
+@pytest.mark.parametrize("k,c", [(1, 512), (1, 32), (10, 7), (3, 6)])
+def test_knn_interpolate_bit_exact(lib, k, c):
+    """Forward bit-exact vs the oracle's restatement of PyG knn_interpolate ((x*w)/w rounding included)."""
+    from myria3d_b200 import ops
+
+    sx, sy = [50, 3, 200], [200, 12, 800]
+    g = torch.Generator().manual_seed(k * 100 + c)
+    pos_x = torch.rand(sum(sx), 3, generator=g)
+    pos_y = torch.rand(sum(sy), 3, generator=g)
+    pos_y[5] = pos_x[7]  # an exact hit: d2 = 0 -> w = 1e16
+    x = torch.randn(sum(sx), c, generator=g)
+    xr = x.clone().requires_grad_(True)
+    ref = O.knn_interpolate(xr, pos_x, pos_y, ptr_of(sx), ptr_of(sy), k, method="brute")
+    go = torch.randn(sum(sy), c, generator=g)
+    ref.backward(go)
+
+    nbr, d2 = ops.knn(pos_x.to(DEV), torch.tensor(ptr_of(sx), device=DEV), pos_y.to(DEV),
+                      torch.tensor(ptr_of(sy), device=DEV), k, max(sy))
+    xg = x.to(DEV).requires_grad_(True)
+    out = ops.knn_interpolate_from_table(xg, nbr, d2, k)
+    out.backward(go.to(DEV))
+    assert torch.equal(out.cpu(), ref.detach()), f"max diff {(out.cpu() - ref.detach()).abs().max()}"
+    assert_close(xg.grad, xr.grad, atol=1e-5, rtol=1e-5, what="interp grad")
