@@ -1,0 +1,144 @@
+"""CPU tests of the host side: C-ABI library loads and exports every declared symbol, host logic
+(BatchNorm fold, decimation bookkeeping, model zoo, Data/Batch), loud failure without a GPU."""
+import os
+import re
+
+import pytest
+import torch
+
+from oracle import randla_oracle as O
+from tests.helpers import assert_close, rand_cloud
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_header_symbol(lib):
+    from myria3d_b200 import _lib
+
+    header = open(os.path.join(ROOT, "include", "b200randla.h")).read()
+    declared = set(re.findall(r"\b(b200_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    assert declared == set(_lib.EXPORTED_SYMBOLS), declared ^ set(_lib.EXPORTED_SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} not exported by libb200randla.so"
+    assert lib.b200_abi_version() == 1 == int(re.search(r"#define B200_ABI_VERSION (\d+)", header).group(1))
+    assert lib.b200_last_error() == b"" or isinstance(lib.b200_last_error(), bytes)
+    assert lib.b200_launch_count() >= 0
+
+
+def test_library_rejects_bad_arguments_without_gpu(lib):
+    """Argument validation happens before any CUDA call: error code + message, no crash."""
+    from myria3d_b200 import _lib
+
+    rc = lib.b200_knn(None, None, 0, None, None, 0, 0, 0, 16, 16, None, None, None)
+    assert rc == 1 and b"null pointer" in lib.b200_last_error()
+    with pytest.raises(ValueError):
+        _lib.check(rc, "b200_knn")
+    rc = lib.b200_lfa_fwd(None, None, None, None, None, None, None, 10, 16, 16, None)
+    assert rc == 1
+
+
+def test_no_cpu_fallback():
+    from myria3d_b200 import B200RandLANet, ops
+
+    net = B200RandLANet(9, 6)
+    x, pos, batch, ptr = rand_cloud([20], seed=0)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        net(x, pos, batch, ptr)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.linear(torch.rand(4, 4), torch.rand(4, 4))
+
+
+def test_fold_encoder_equals_linear_plus_batchnorm():
+    """BN-moment trick: folded affine map of q=(p_i,p_j,dist) == Linear(10->h) +
+    train-mode BatchNorm over all edges, values AND gradients AND running statistics (pure torch, CPU)."""
+    from myria3d_b200.randla_net import SharedMLP, fold_encoder
+
+    _, pos, _, ptr = rand_cloud([60, 7], seed=4)
+    ei = O.knn_graph(pos, 16, ptr.tolist(), "brute")
+    j, i = ei
+    d = pos[j] - pos[i]
+    dist = torch.sqrt((d * d).sum(1, keepdim=True))
+    r = torch.cat([pos[i], pos[j], d, dist], 1)
+    q = torch.cat([pos[i], pos[j], dist], 1)
+    e = q.shape[0]
+    qd = q.double()
+    moments = torch.cat([torch.tensor([float(e)], dtype=torch.float64), qd.sum(0), (qd.t() @ qd).flatten()])
+
+    for training in (True, False):
+        ref = O.SharedMLP([10, 8])
+        g = torch.Generator().manual_seed(1)
+        bn = ref.norms[0].module
+        bn.weight.data.uniform_(0.5, 1.5, generator=g), bn.bias.data.uniform_(-0.5, 0.5, generator=g)
+        bn.running_mean.uniform_(-0.3, 0.3, generator=g), bn.running_var.uniform_(0.5, 1.5, generator=g)
+        enc = SharedMLP([10, 8])
+        enc.load_state_dict(ref.state_dict())
+        ref.train(training), enc.train(training)
+        ref.act = False  # compare pre-activation
+        z_ref = ref(r)
+        w, b = fold_encoder(enc, moments, e, training)
+        z = q @ w.t() + b
+        assert_close(z, z_ref, atol=2e-5, what="folded encoder output")
+        go = torch.randn(e, 8, generator=g)
+        z_ref.backward(go)
+        z.backward(go)
+        for (n1, p1), (_, p2) in zip(enc.named_parameters(), ref.named_parameters()):
+            assert_close(p1.grad, p2.grad, atol=2e-4, rtol=2e-4, what=f"fold grad {n1}")
+        for (n1, b1), (_, b2) in zip(enc.named_buffers(), ref.named_buffers()):
+            assert_close(b1, b2, atol=1e-6, rtol=1e-5, what=f"fold buffer {n1}")
+
+
+def test_decimation_bookkeeping_and_errors():
+    from myria3d_b200.randla_net import B200RandLANet, _Level, decimation_indices, decimation_sizes
+
+    assert decimation_sizes([0, 12800, 12850, 12851], 4) == [0, 3200, 3212, 3213]
+    with pytest.raises(ValueError, match="decimation_factor"):
+        decimation_sizes([0, 10], 0)
+    torch.manual_seed(3)
+    idx, new_ptr = decimation_indices([0, 50, 53], 4, torch.device("cpu"))
+    torch.manual_seed(3)
+    idx_ref, ptr_ref = O.decimation_indices([0, 50, 53], 4)
+    assert torch.equal(idx, idx_ref) and new_ptr == ptr_ref  # same RNG stream as the reference's loop
+    lvl = _Level([0, 50, 53], torch.device("cpu"))
+    assert lvl.max_n == 50 and lvl.num_edges(16) == 50 * 16 + 3 * 3
+    with pytest.raises(ValueError):
+        B200RandLANet(9, 6, num_neighbors=64)
+
+
+def test_model_zoo_and_wrapper_surface():
+    from myria3d_b200 import MODEL_ZOO, B200RandLANet, Model, get_neural_net_class
+
+    assert get_neural_net_class("B200RandLANet") is B200RandLANet
+    assert get_neural_net_class("RandLANet") is B200RandLANet  # substring match like models/model.py:26-28
+    with pytest.raises(KeyError):
+        get_neural_net_class("PyGRandLANet")  # the stock name keeps selecting the reference class
+    m = Model(neural_net_class_name="B200RandLANet", neural_net_hparams=dict(num_features=2, num_classes=7),
+              criterion=torch.nn.CrossEntropyLoss(ignore_index=65), lr=1e-3,
+              optimizer=lambda params, lr: torch.optim.Adam(params, lr=lr), lr_scheduler=None, monitor="val/loss")
+    assert isinstance(m.model, B200RandLANet) and m.model.fc0.weight.shape == (32, 2)
+    assert all(k.startswith("model.") for k in m.state_dict() if "criterion" not in k)
+    assert isinstance(m.configure_optimizers(), torch.optim.Adam)
+    t = m._get_batch_tensor_by_enumeration([torch.zeros(3, 3), torch.zeros(2, 3)])
+    assert t.tolist() == [0, 0, 0, 1, 1]
+    for name in ("forward", "training_step", "validation_step", "test_step", "predict_step", "configure_optimizers"):
+        assert callable(getattr(m, name))
+
+
+def test_data_batch_standins():
+    from myria3d_b200 import Batch, Data
+
+    ds = [Data(x=torch.rand(n, 9), pos=torch.rand(n, 3), y=torch.zeros(n, dtype=torch.long)) for n in (5, 3)]
+    b = Batch.from_data_list(ds + [None])  # None-proof like GeometricNoneProofCollater
+    assert b.ptr.tolist() == [0, 5, 8] and b.batch.tolist() == [0] * 5 + [1] * 3 and b.num_graphs == 2
+    assert "copies" not in b and "x" in b
+    b.copies = {"pos_copy": torch.rand(4, 3)}
+    assert "copies" in b and b.to("cpu").copies["pos_copy"].shape == (4, 3)
+
+
+def test_state_dict_keys_match_oracle():
+    from myria3d_b200 import B200RandLANet
+
+    a = B200RandLANet(9, 7).state_dict()
+    b = O.OracleRandLANet(9, 7).state_dict()
+    assert list(a.keys()) == list(b.keys())
+    assert all(a[k].shape == b[k].shape and a[k].dtype == b[k].dtype for k in a)

@@ -1,0 +1,146 @@
+"""CPU tests of the oracle (the checker) against the committed golden vectors and the reference's
+structural pins (shipped checkpoint, shape tests).  No GPU, no CUDA library calls."""
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import randla_oracle as O
+from oracle.gen_golden import build_net, weight_checksum
+from tests.helpers import assert_close, ptr_of, rand_cloud
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "randla_small.pt")
+CKPT = "/root/reference/trained_model_assets/proto151_V2.0_epoch_100_Myria3DV3.1.0.ckpt"
+
+
+def test_oracle_matches_golden_vectors():
+    g = torch.load(GOLDEN)
+    net = build_net(g["seed"])
+    assert abs(weight_checksum(net) - g["weight_checksum"]) < 1e-6 * g["weight_checksum"], "seeded init drifted"
+    net.eval()
+    with torch.no_grad():
+        logits = net(g["x"], g["pos"], g["batch"], g["ptr"], decimation_idx=g["decimation_idx"])
+    assert_close(logits, g["logits_eval"], atol=1e-5, what="eval logits vs golden")
+    knn0 = O.knn_kdtree(g["pos"], g["ptr"].tolist(), g["pos"], g["ptr"].tolist(), 16)[0]
+    assert torch.equal(knn0.int(), g["knn_level0"])
+
+    net = build_net(g["seed"])
+    net.train()
+    net.mlp_classif.injected_masks = [None, g["dropout_mask"]]
+    logits = net(g["x"], g["pos"], g["batch"], g["ptr"], decimation_idx=g["decimation_idx"])
+    loss = F.cross_entropy(logits, g["y"], ignore_index=65)
+    loss.backward()
+    assert_close(logits, g["logits_train"], atol=1e-5, what="train logits vs golden")
+    assert abs(float(loss) - g["loss"]) < 1e-5
+    params = dict(net.named_parameters())
+    for k, v in g["grads"].items():
+        assert_close(params[k].grad, v, atol=1e-6, rtol=1e-3, what=f"grad {k}")
+    bufs = dict(net.named_buffers())
+    for k, v in g["buffers_after_step"].items():
+        assert_close(bufs[k], v, atol=1e-6, rtol=1e-5, what=k)
+
+
+@pytest.mark.skipif(not os.path.exists(CKPT), reason="reference checkpoint not on this box")
+def test_oracle_and_product_strict_load_shipped_checkpoint():
+    """State-dict contract: 257 entries, 1 113 719 trainable parameters."""
+    from myria3d_b200 import B200RandLANet
+    from myria3d_b200.ckpt import load_lightning_checkpoint, net_state_dict
+
+    ck = load_lightning_checkpoint(CKPT)
+    sd = net_state_dict(ck)
+    assert len(sd) == 257
+    for cls in (O.OracleRandLANet, B200RandLANet):
+        net = cls(9, 7, return_logits=True)
+        res = net.load_state_dict(sd, strict=True)
+        assert not res.missing_keys and not res.unexpected_keys
+        assert sum(p.numel() for p in net.parameters()) == 1113719
+    # the trained weights give finite, confident predictions on a synthetic tile
+    net = O.OracleRandLANet(9, 7, return_logits=True)
+    net.load_state_dict(sd)
+    net.eval()
+    x, pos, y, batch, ptr = O.synthetic_batch([2000], seed=1, num_classes=7)
+    with torch.no_grad():
+        out = net(x, pos, batch, ptr)
+    assert out.shape == (2000, 7) and torch.isfinite(out).all()
+
+
+@pytest.mark.parametrize("num_nodes", [[1250, 1250], [50, 50], [1250, 1000]])
+def test_fake_run_oracle(num_nodes):
+    """tests/myria3d/models/modules/test_randla_nets.py:8-40 on the oracle (sizes /10 for CPU time;
+    the 12 500-point originals run on the GPU suite)."""
+    x, pos, batch, ptr = rand_cloud(num_nodes, seed=3)
+    model = O.OracleRandLANet(9, 6, decimation=4, num_neighbors=16)
+    out = model(x, pos, batch, ptr)
+    assert out.shape == torch.Size([sum(num_nodes), 6])
+    assert [t.numel() for t in model.last_decimation_idx][-1] >= len(num_nodes)
+
+
+def test_knn_kdtree_equals_bruteforce_and_tie_rule():
+    sx, sy = [400, 3, 1], [900, 10, 2]
+    g = torch.Generator().manual_seed(0)
+    px, py = torch.rand(sum(sx), 3, generator=g), torch.rand(sum(sy), 3, generator=g)
+    for k in (1, 10, 16):
+        a, da = O.knn_bruteforce(px, ptr_of(sx), py, ptr_of(sy), k)
+        b, db = O.knn_kdtree(px, ptr_of(sx), py, ptr_of(sy), k)
+        assert torch.equal(a, b) and torch.equal(da, db)
+        assert (da == torch.tensor([min(k, 400)] * 900 + [min(k, 3)] * 10 + [1] * 2)).all()
+    # duplicates: equal distances resolve to the lower index
+    p = torch.tensor([[0.0, 0, 0], [1, 0, 0], [1, 0, 0], [1, 0, 0], [5, 5, 5]])
+    nb, _ = O.knn_bruteforce(p, [0, 5], p[:1], [0, 1], 3)
+    assert nb.tolist() == [[0, 1, 2]]
+    nb, _ = O.knn_kdtree(p, [0, 5], p[:1], [0, 1], 3, extra=1)
+    assert nb.tolist() == [[0, 1, 2]]
+
+
+def test_knn_graph_layout():
+    _, pos, _, ptr = rand_cloud([30, 5], seed=1)
+    ei = O.knn_graph(pos, 16, ptr.tolist(), "brute")
+    assert ei.shape == (2, 30 * 16 + 5 * 5)
+    assert (ei[1][1:] >= ei[1][:-1]).all()  # grouped by centre
+    assert (ei[0][ei[1] < 30] < 30).all() and (ei[0][ei[1] >= 30] >= 30).all()
+    first = torch.cat([torch.tensor([True]), ei[1][1:] != ei[1][:-1]])
+    assert torch.equal(ei[0][first], ei[1][first])  # nearest neighbour is the point itself (loop=True)
+
+
+def test_pyg_softmax_and_scatter():
+    src = torch.randn(10, 4)
+    index = torch.tensor([0, 0, 0, 1, 1, 2, 2, 2, 2, 2])
+    out = O.pyg_softmax(src, index, 3)
+    for gidx in range(3):
+        m = index == gidx
+        assert_close(out[m], torch.softmax(src[m], dim=0), atol=1e-6, what="softmax group")
+    assert_close(O.scatter_sum(src, index, 3)[2], src[5:].sum(0), atol=1e-6)
+    assert_close(O.scatter_max(src, index, 3)[0], src[:3].max(0).values, atol=0)
+
+
+def test_decimation_indices_contract():
+    torch.manual_seed(0)
+    idx, new_ptr = O.decimation_indices([0, 100, 103, 104], 4)
+    assert new_ptr == [0, 25, 26, 27]  # max(1, n // 4): clouds never vanish
+    assert idx[:25].max() < 100 and idx[25] >= 100 and idx[25] < 103 and idx[26] == 103
+    assert len(set(idx.tolist())) == 27
+    with pytest.raises(ValueError):
+        O.decimation_indices([0, 10], 0.5)
+
+
+def test_knn_interpolate_k1_is_not_a_pure_gather():
+    """(x*w)/w of PyG's knn_interpolate rounds twice: a few elements differ by 1 ulp from x[nn]."""
+    g = torch.Generator().manual_seed(0)
+    px, py = torch.rand(50, 3, generator=g), torch.rand(400, 3, generator=g)
+    x = torch.randn(50, 64, generator=g)
+    y = O.knn_interpolate(x, px, py, [0, 50], [0, 400], 1, "brute")
+    nn, _ = O.knn_bruteforce(px, [0, 50], py, [0, 400], 1)
+    gathered = x[nn[:, 0]]
+    assert_close(y, gathered, atol=1e-6, what="interp vs gather")
+    assert (y != gathered).any()
+
+
+def test_block1_net_config_a_runs():
+    """BASELINE configs[0]: 1 encoder layer, K=16, 4096 pts/tile, 6 classes, batch 2 -- CPU path."""
+    x, pos, y, batch, ptr = O.synthetic_batch([4096, 4096])
+    net = O.OracleBlock1Net(9, 6)
+    out = net(x, pos, batch, ptr)
+    loss = F.cross_entropy(out, y)
+    loss.backward()
+    assert out.shape == (8192, 6) and torch.isfinite(loss)

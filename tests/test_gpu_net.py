@@ -192,3 +192,43 @@ def test_checkpoint_state_dict_and_model_wrapper(lib):
     assert targets is None and logits_full.shape == (2900, 7)
     pred = model.predict_step(batch.to(DEV))
     assert pred["logits"].device.type == "cpu" and pred["logits"].shape == (2900, 7)
+
+
+def test_against_committed_golden_vectors(lib):
+    """CUDA path vs tests/golden/randla_small.pt (oracle outputs committed by oracle/gen_golden.py)."""
+    import os
+
+    from myria3d_b200 import B200RandLANet
+    from oracle.gen_golden import build_net
+
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "randla_small.pt"))
+    net = B200RandLANet(9, 6, num_neighbors=16, return_logits=True)
+    net.load_state_dict(build_net(g["seed"]).state_dict(), strict=True)
+    net.to(DEV)
+    args = [g[k].to(DEV) for k in ("x", "pos", "batch", "ptr")]
+    net.injected_decimation_idx = g["decimation_idx"]
+
+    from myria3d_b200 import ops
+
+    nbr, _ = ops.knn(args[1], args[3], args[1], args[3], 16, max(g["sizes"]), kt=16)
+    assert torch.equal(nbr.cpu(), g["knn_level0"]), "level-0 kNN table differs from the golden one"
+
+    net.eval()
+    with torch.no_grad():
+        logits = net(*args)
+    assert_close(logits, g["logits_eval"], atol=LOGIT_TOL, what="eval logits vs golden")
+
+    net.load_state_dict(build_net(g["seed"]).state_dict(), strict=True)
+    net.train()
+    net.mlp_classif.injected_masks = [None, g["dropout_mask"].to(DEV)]
+    logits = net(*args)
+    loss = F.cross_entropy(logits, g["y"].to(DEV), ignore_index=65)
+    loss.backward()
+    assert_close(logits, g["logits_train"], atol=LOGIT_TOL, what="train logits vs golden")
+    assert abs(float(loss.detach()) - g["loss"]) < 1e-4
+    params = dict(net.named_parameters())
+    for k, v in g["grads"].items():
+        assert rel_err(params[k].grad, v) < 1e-3, f"grad {k}"
+    bufs = dict(net.named_buffers())
+    for k, v in g["buffers_after_step"].items():
+        assert_close(bufs[k], v, atol=1e-5, rtol=1e-4, what=k)
