@@ -51,6 +51,9 @@ def parse_args():
     ap.add_argument("--cpu-steps", type=int, default=5)
     ap.add_argument("--profile-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--eager", action="store_true", help="launch every kernel from Python instead of replaying the step graph")
+    ap.add_argument("--decimation-rng", choices=["fused", "reference"], default="fused",
+                    help="fused: one batched random draw per level; reference: per-cloud torch.randperm like the reference")
     ap.add_argument("--kernel-report", default=None, help="write the per-kernel table (JSON) here")
     return ap.parse_args()
 
@@ -136,6 +139,9 @@ def algorithmic_bytes(name: str, a):
     if name == "b200_knn":
         nx, ny, _clouds, _maxq, k, kt = a
         return nx * 12 + ny * (12 + 4 * kt)
+    if name == "b200_knn_grid":
+        nx, ny, _clouds, _mx, _my, k, kt, _ws = a
+        return nx * 12 + ny * (12 + 4 * kt)
     if name == "b200_edge_moments":
         n, kt = a
         return n * (12 + 4 * kt)
@@ -189,7 +195,6 @@ def cpu_reference(tiles: int, points: int, steps: int, warmup: int):
     from oracle import randla_oracle as O
 
     cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     torch.manual_seed(12345)
     net = O.OracleRandLANet(NUM_FEATURES, NUM_CLASSES, decimation=DECIMATION, num_neighbors=K_NEIGHBORS,
                             return_logits=True)
@@ -204,7 +209,23 @@ def cpu_reference(tiles: int, points: int, steps: int, warmup: int):
         loss = F.cross_entropy(logits, y, ignore_index=65)
         loss.backward()
         opt.step()
-        return float(loss)
+        return float(loss.detach())
+
+    # "all the host threads it can use": torch's intra-op pool is NOT monotone in the thread count on
+    # many-core hosts (the [N, c] ops here are small), so take the fastest of a few pool sizes.
+    candidates = sorted({min(cores, t) for t in (8, 16, 32)})  # >32 threads measured 10-25x SLOWER on the 128-core box
+    best_t, best_dt = candidates[0], float("inf")
+    torch.set_num_threads(candidates[0])
+    step()  # lazy initialisation (first call is several times slower)
+    for t in candidates:
+        torch.set_num_threads(t)
+        step()
+        t0 = time.perf_counter()
+        step()
+        dt = time.perf_counter() - t0
+        if dt < best_dt:
+            best_t, best_dt = t, dt
+    torch.set_num_threads(best_t)
 
     for _ in range(warmup):
         step()
@@ -214,7 +235,8 @@ def cpu_reference(tiles: int, points: int, steps: int, warmup: int):
     dt = (time.perf_counter() - t0) / max(steps, 1)
     return {"value": tiles * points / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
             "sample": f"{tiles} tiles x {points} pts per step, {warmup} warm-up + {steps} timed steps, "
-                      f"oracle/randla_oracle.py (pure torch CPU + scipy cKDTree, 1 kNN worker)",
+                      f"oracle/randla_oracle.py (pure torch CPU + scipy cKDTree, 1 kNN worker); "
+                      f"{best_t} torch threads = fastest of {candidates} on a {cores}-core host",
             "ms_per_step": dt * 1e3}
 
 
@@ -227,7 +249,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, 1),
+        "config": workload_config(args, 1, "reference"),
         "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -235,14 +257,17 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(args, world):
+def workload_config(args, world, impl="b200"):
     return {
         "workload": f"RandLA-Net full (4 down/4 up), K={K_NEIGHBORS}, {args.points} pts/tile, batch={args.tiles}/GPU "
                     f"(BASELINE configs[1]{'/[2]' if world > 1 else ''})",
-        "step": "fwd + CrossEntropyLoss + bwd + flat NCCL grad all-reduce (N>1) + Adam",
+        "step": "fwd + CrossEntropyLoss + bwd + flat NCCL grad all-reduce (N>1) + Adam; "
+                + ("reference CPU path: eager PyTorch, bounded sample of "
+                   f"{args.cpu_tiles} tiles per step" if impl == "reference" else
+                   ("eager launches" if args.eager else "whole step replayed as one CUDA graph (GraphedTrainStep)")),
         "num_features": NUM_FEATURES, "num_classes": NUM_CLASSES, "global_batch_tiles": args.tiles * world,
         "points_per_step": args.tiles * args.points * world,
-        "parallelism": f"dp{world}", "l2": "256 MiB buffer rewritten between timed steps (outside the event pairs); "
+        "decimation_rng": args.decimation_rng, "parallelism": f"dp{world}", "l2": "256 MiB buffer rewritten between timed steps (outside the event pairs); "
                                            "4 rotating input batches",
     }
 
@@ -261,6 +286,7 @@ def run_b200(args):
 
     from myria3d_b200 import Model, _lib
     from myria3d_b200.build import build_library
+    from myria3d_b200.graphed import GraphedTrainStep
     from myria3d_b200.parallel import FlatGradAllReducer, broadcast_module_state
 
     if rank == 0:
@@ -278,7 +304,9 @@ def run_b200(args):
     model.train()
     broadcast_module_state(model)
     reducer = FlatGradAllReducer(model)
-    opt = torch.optim.Adam(model.parameters(), lr=LR)
+    opt = torch.optim.Adam(model.parameters(), lr=LR, capturable=not args.eager, fused=True)
+    model.model.decimation_rng = args.decimation_rng
+    graphed = None if args.eager else GraphedTrainStep(model, opt, reducer, decimation_rng=args.decimation_rng)
 
     n_rot = 4
     host = [host_batch(args.tiles, args.points, 12345 + 1000 * rank + 100 * r).pin_memory() for r in range(n_rot)]
@@ -288,6 +316,11 @@ def run_b200(args):
     points_per_step = args.tiles * args.points
 
     def train_step(batch):
+        if graphed is not None:
+            return graphed(batch)
+        return eager_step(batch)
+
+    def eager_step(batch):
         reducer.zero_grad()
         out = model.training_step(batch, 0)
         out["loss"].backward()
@@ -331,11 +364,14 @@ def run_b200(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    launches0 = _lib.launch_count()
+    def launches_now():
+        return graphed.library_launches if graphed is not None else _lib.launch_count()
+
+    launches0 = launches_now()
     barrier()
     total_ms = timed("resident", args.steps)
     barrier()
-    launches = (_lib.launch_count() - launches0) // max(args.steps, 1)
+    launches = (launches_now() - launches0) // max(args.steps, 1)
     total_ms = max_over_ranks(total_ms)
     # ---- end-to-end through Model.training_step with host batches
     for s in range(2):
@@ -352,7 +388,7 @@ def run_b200(args):
         prof = _lib.KernelProfiler()
         _lib.PROFILER = prof
         for s in range(args.profile_steps):
-            train_step(resident[s % n_rot])
+            eager_step(resident[s % n_rot])  # eager: CUDA events around every library call
         _lib.PROFILER = None
         recs = prof.summary()
         table = kernel_table([(n, i, ms / 1.0) for n, i, ms in recs])

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define B200_ABI_VERSION 1
+#define B200_ABI_VERSION 2
 
 #define B200_OK 0
 #define B200_E_INVALID 1     /* bad argument (null pointer, unsupported size/alignment) */
@@ -59,6 +59,19 @@ int b200_knn(const float* pos_x, const int64_t* ptr_x, int64_t nx,
              int32_t num_clouds, int64_t max_queries_per_cloud,
              int32_t k, int32_t kt, int32_t* nbr, float* dist2, void* stream);
 
+/* Same contract and bit-identical output as b200_knn, but each query only visits the cells of a per-cloud
+ * uniform 2-D bucket grid (over the two widest axes) that can still contain one of its k nearest
+ * neighbours: O(n k) instead of O(n^2) distance evaluations.  Needs a caller-owned, 256-byte aligned
+ * workspace of b200_knn_grid_workspace_bytes(nx, num_clouds, max_x_per_cloud) bytes (contents are
+ * scratch).  max_x_per_cloud / max_y_per_cloud must be the exact maxima of the cloud sizes (or larger).
+ */
+int64_t b200_knn_grid_workspace_bytes(int64_t nx, int32_t num_clouds, int64_t max_x_per_cloud);
+int b200_knn_grid(const float* pos_x, const int64_t* ptr_x, int64_t nx,
+                  const float* pos_y, const int64_t* ptr_y, int64_t ny,
+                  int32_t num_clouds, int64_t max_x_per_cloud, int64_t max_y_per_cloud,
+                  int32_t k, int32_t kt, int32_t* nbr, float* dist2,
+                  void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------- LocSE / attentive pooling -----
  * Together these replace LocalFeatureAggregation.propagate()+message()
  * (myria3d/models/modules/pyg_randla_net.py:121-152): gather, relative position
@@ -73,6 +86,24 @@ int b200_knn(const float* pos_x, const int64_t* ptr_x, int64_t nx,
  */
 int b200_edge_moments(const float* pos, const int32_t* nbr, int64_t n, int32_t kt,
                       double* out, void* stream);
+
+/* Fold mlp_encoder = Linear(10 -> h) + BatchNorm1d(momentum .01, eps 1e-6) (pyg_randla_net.py:117,144)
+ * into the affine map of q the fused kernels consume:  enc_w [h,7], enc_b [h].
+ *   w fp32 [h,10], b fp32 [h] or NULL, gamma/beta fp32 [h] (BatchNorm affine),
+ *   moments fp64 [57] from b200_edge_moments (training) or NULL (eval: running statistics are used).
+ * Training also updates running_mean / running_var (unbiased variance) and increments
+ * *num_batches_tracked (int64, may be NULL) exactly like torch.nn.BatchNorm1d.
+ * The backward returns the exact train-mode gradients through the batch statistics:
+ *   grad_w [h,10], grad_b [h] (may be NULL; identically 0 in training), grad_gamma, grad_beta (written). */
+int b200_encoder_fold_fwd(const float* w, const float* b, const float* gamma, const float* beta,
+                          const double* moments, float* running_mean, float* running_var,
+                          int64_t* num_batches_tracked, float momentum, float eps,
+                          float* enc_w, float* enc_b, int32_t h, void* stream);
+int b200_encoder_fold_bwd(const float* w, const float* b, const float* gamma, const double* moments,
+                          const float* running_mean, const float* running_var, float eps,
+                          const float* g_enc_w, const float* g_enc_b,
+                          float* grad_w, float* grad_b, float* grad_gamma, float* grad_beta,
+                          int32_t h, void* stream);
 
 /* Fused forward.  c = channels of the LFA (x has h = c/2 features).
  *   x       fp32 [n, h]        pos fp32 [n, 3]      nbr int32 [n, kt]
@@ -150,9 +181,11 @@ int b200_linear_bwd_weight(const float* grad_y, const float* a1, int64_t ld1, in
  * over `count` rows.  Writes scale = gamma*invstd, shift = beta - mean*scale, and
  * mean / invstd (saved for backward).  If running_mean != NULL updates the running
  * statistics in place: r = (1-momentum) r + momentum * stat (unbiased variance).
+ * and increments *num_batches_tracked (int64, may be NULL).
  * With colstats == NULL (eval mode) uses the running statistics instead. */
 int b200_bn_finalize(const double* colstats, int64_t count, const float* gamma, const float* beta,
-                     float* running_mean, float* running_var, float momentum, float eps,
+                     float* running_mean, float* running_var, int64_t* num_batches_tracked,
+                     float momentum, float eps,
                      float* scale, float* shift, float* mean, float* invstd, int32_t c, void* stream);
 
 /* out = act(y1*scale1 + shift1 [+ y2*scale2 + shift2]) ; act = LeakyReLU(slope) (slope = 1: identity). */

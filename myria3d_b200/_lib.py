@@ -20,6 +20,9 @@ _SIGNATURES = {
     "b200_launch_count": (c_int64, []),
     "b200_check_device": (c_int, []),
     "b200_knn": (c_int, [_P, _P, c_int64, _P, _P, c_int64, c_int32, c_int64, c_int32, c_int32, _P, _P, _P]),
+    "b200_knn_grid_workspace_bytes": (c_int64, [c_int64, c_int32, c_int64]),
+    "b200_knn_grid": (c_int, [_P, _P, c_int64, _P, _P, c_int64, c_int32, c_int64, c_int64, c_int32, c_int32, _P, _P, _P,
+                              c_int64, _P]),
     "b200_edge_moments": (c_int, [_P, _P, c_int64, c_int32, _P, _P]),
     "b200_lfa_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int64, c_int32, c_int32, _P]),
     "b200_lfa_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int32, c_int32, _P]),
@@ -30,7 +33,9 @@ _SIGNATURES = {
     "b200_linear_fwd": (c_int, [_P, c_int64, c_int32, _P, c_int64, c_int32, _P, _P, _P, c_int64, c_int32, _P, _P]),
     "b200_linear_bwd_input": (c_int, [_P, _P, _P, c_int64, c_int32, _P, c_int64, c_int32, c_int64, c_int32, _P]),
     "b200_linear_bwd_weight": (c_int, [_P, _P, c_int64, c_int32, _P, c_int64, c_int32, _P, _P, c_int64, c_int32, _P]),
-    "b200_bn_finalize": (c_int, [_P, c_int64, _P, _P, _P, _P, c_float, c_float, _P, _P, _P, _P, c_int32, _P]),
+    "b200_bn_finalize": (c_int, [_P, c_int64, _P, _P, _P, _P, _P, c_float, c_float, _P, _P, _P, _P, c_int32, _P]),
+    "b200_encoder_fold_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_float, c_float, _P, _P, c_int32, _P]),
+    "b200_encoder_fold_bwd": (c_int, [_P, _P, _P, _P, _P, _P, c_float, _P, _P, _P, _P, _P, _P, c_int32, _P]),
     "b200_affine_act_fwd": (c_int, [_P, _P, _P, _P, _P, _P, c_float, _P, c_int64, c_int32, _P]),
     "b200_affine_act_bwd_reduce": (c_int, [_P, _P, c_float, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int32, _P]),
     "b200_affine_act_bwd_apply": (
@@ -39,7 +44,7 @@ _SIGNATURES = {
     ),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _lib = None
 

@@ -273,9 +273,10 @@ linear_bwd_weight_kernel(const float* __restrict__ gy, bool gvec, CatRows A, flo
 // ------------------------------------------------------------------ BatchNorm finalisation
 __global__ void bn_finalize_kernel(const double* __restrict__ colstats, int64_t count, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, float* __restrict__ running_mean,
-                                   float* __restrict__ running_var, float momentum, float eps,
-                                   float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
+                                   float* __restrict__ running_var, int64_t* __restrict__ num_batches_tracked,
+                                   float momentum, float eps, float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
                                    float* __restrict__ invstd_out, int c) {
+  if (blockIdx.x == 0 && threadIdx.x == 0 && colstats && num_batches_tracked) *num_batches_tracked += 1;
   for (int ch = blockIdx.x * blockDim.x + threadIdx.x; ch < c; ch += gridDim.x * blockDim.x) {
     double mean, var;
     if (colstats) {
@@ -559,8 +560,9 @@ extern "C" int b200_linear_bwd_weight(const float* grad_y, const float* a1, int6
 }
 
 extern "C" int b200_bn_finalize(const double* colstats, int64_t count, const float* gamma, const float* beta,
-                                float* running_mean, float* running_var, float momentum, float eps, float* scale,
-                                float* shift, float* mean, float* invstd, int32_t c, void* stream) {
+                                float* running_mean, float* running_var, int64_t* num_batches_tracked, float momentum,
+                                float eps, float* scale, float* shift, float* mean, float* invstd, int32_t c,
+                                void* stream) {
   B200_REQUIRE(gamma && beta && scale && shift && c > 0, B200_E_INVALID, "b200_bn_finalize: null pointer / c <= 0");
   B200_REQUIRE(colstats || (running_mean && running_var), B200_E_INVALID,
                "b200_bn_finalize: eval mode needs running statistics");
@@ -568,7 +570,8 @@ extern "C" int b200_bn_finalize(const double* colstats, int64_t count, const flo
   B200_REQUIRE((running_mean == nullptr) == (running_var == nullptr), B200_E_INVALID,
                "b200_bn_finalize: running_mean / running_var must come together");
   bn_finalize_kernel<<<(unsigned)ceil_div(c, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
-      colstats, count, gamma, beta, running_mean, running_var, momentum, eps, scale, shift, mean, invstd, c);
+      colstats, count, gamma, beta, running_mean, running_var, num_batches_tracked, momentum, eps, scale, shift, mean,
+      invstd, c);
   B200_CHECK_LAUNCH("bn_finalize_kernel");
   return B200_OK;
 }

@@ -90,7 +90,10 @@ class Model(_Base):
         ptr_y = torch.tensor(ptr_y_host, dtype=torch.int64, device=dev)
         ptr_x = batch.ptr.to(dev, torch.int64)
         k = int(getattr(self.hparams, "interpolation_k", 10))
-        nbr, dist2 = ops.knn(pos_sub, ptr_x, pos_full, ptr_y, k, max(sizes_y) if sizes_y else 0, kt=k)
+        ptr_x_host = batch.ptr.tolist()
+        max_x = max((int(ptr_x_host[i + 1]) - int(ptr_x_host[i]) for i in range(len(ptr_x_host) - 1)), default=0)
+        nbr, dist2 = ops.knn(pos_sub, ptr_x, pos_full, ptr_y, k, max(sizes_y) if sizes_y else 0, kt=k,
+                             max_points_per_cloud=max_x)
         logits = ops.knn_interpolate_from_table(logits, nbr, dist2, k)
         targets = None
         if "transformed_y_copy" in copies:

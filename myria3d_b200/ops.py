@@ -67,24 +67,47 @@ def table_width(k: int) -> int:
 
 
 # ------------------------------------------------------------------------------------------- kNN
+GRID_KNN_MIN_POINTS = 512  # clouds at least this large use the bucket-grid search
+
+
 def knn(pos_x: Tensor, ptr_x: Tensor, pos_y: Tensor, ptr_y: Tensor, k: int, max_queries_per_cloud: int,
-        kt: Optional[int] = None, want_dist: bool = True) -> Tuple[Tensor, Optional[Tensor]]:
+        kt: Optional[int] = None, want_dist: bool = True, max_points_per_cloud: Optional[int] = None,
+        algo: str = "auto") -> Tuple[Tensor, Optional[Tensor]]:
     """k nearest ``pos_x`` points of the same cloud for every ``pos_y`` point.
 
     Stands for torch_cluster ``knn`` behind ``knn_graph`` (pyg_randla_net.py:180) and
     ``knn_interpolate`` (pyg_randla_net.py:250, models/model.py:90).  Returns ``nbr`` int32
     ``[ny, kt]`` (-1 padded) and ``dist2`` fp32 ``[ny, kt]`` (inf padded).
+
+    ``algo``: ``"brute"`` = tiled brute force (TMA-staged candidate tiles), ``"grid"`` = bucket-grid ring
+    search, ``"auto"`` = grid when the largest candidate cloud has >= ``GRID_KNN_MIN_POINTS`` points.
+    Both are exact and return identical tables.  ``max_points_per_cloud`` (largest ``pos_x`` cloud)
+    defaults to ``max_queries_per_cloud`` (right for self-queries).
     """
     _need_cuda(pos_x, ptr_x, pos_y, ptr_y)
     kt = k if kt is None else kt
-    pos_x, pos_y = _f32c(pos_x), _f32c(pos_y)
+    same = pos_x is pos_y and ptr_x is ptr_y
+    pos_x = _f32c(pos_x)
+    pos_y = pos_x if same else _f32c(pos_y)
     ptr_x = ptr_x.to(torch.int64).contiguous()
-    ptr_y = ptr_y.to(torch.int64).contiguous()
-    ny = pos_y.shape[0]
+    ptr_y = ptr_x if same else ptr_y.to(torch.int64).contiguous()
+    max_x = int(max_queries_per_cloud if max_points_per_cloud is None else max_points_per_cloud)
+    ny, nx = pos_y.shape[0], pos_x.shape[0]
+    num_clouds = ptr_x.numel() - 1
     nbr = torch.empty((ny, kt), dtype=torch.int32, device=pos_y.device)
     dist2 = torch.empty((ny, kt), dtype=torch.float32, device=pos_y.device) if want_dist else None
-    _call("b200_knn", _p(pos_x), _p(ptr_x), pos_x.shape[0], _p(pos_y), _p(ptr_y), ny,
-                              ptr_x.numel() - 1, int(max_queries_per_cloud), k, kt, _p(nbr), _p(dist2), _stream())
+    if algo == "auto":
+        algo = "grid" if max_x >= GRID_KNN_MIN_POINTS else "brute"
+    if algo == "grid":
+        nbytes = int(_lib.load().b200_knn_grid_workspace_bytes(nx, num_clouds, max_x))
+        ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=pos_x.device)
+        _call("b200_knn_grid", _p(pos_x), _p(ptr_x), nx, _p(pos_y), _p(ptr_y), ny, num_clouds, max_x,
+              int(max_queries_per_cloud), k, kt, _p(nbr), _p(dist2), _p(ws), nbytes, _stream())
+    elif algo == "brute":
+        _call("b200_knn", _p(pos_x), _p(ptr_x), nx, _p(pos_y), _p(ptr_y), ny, num_clouds,
+              int(max_queries_per_cloud), k, kt, _p(nbr), _p(dist2), _stream())
+    else:
+        raise ValueError(f"unknown kNN algorithm {algo!r}")
     return nbr, dist2
 
 
@@ -94,6 +117,51 @@ def edge_moments(pos: Tensor, nbr: Tensor) -> Tensor:
     out = torch.zeros(57, dtype=torch.float64, device=pos.device)
     _call("b200_edge_moments", _p(pos), _p(nbr), pos.shape[0], nbr.shape[1], _p(out), _stream())
     return out
+
+
+# ------------------------------------------------------------------ encoder fold (Linear + BatchNorm -> affine)
+class _EncoderFold(torch.autograd.Function):
+    """mlp_encoder = Linear(10->h) + BatchNorm1d over all E edges (pyg_randla_net.py:117,144) folded into the
+    affine map of q = (p_i, p_j, dist) that the fused LFA kernels consume; exact train-mode gradients."""
+
+    @staticmethod
+    def forward(ctx, w, b, gamma, beta, moments, rm, rv, nbt, momentum, eps):
+        w, gamma, beta = _f32c(w), _f32c(gamma), _f32c(beta)
+        b = _f32c(b) if b is not None else None
+        h = w.shape[0]
+        enc_w = torch.empty((h, 7), dtype=torch.float32, device=w.device)
+        enc_b = torch.empty(h, dtype=torch.float32, device=w.device)
+        _call("b200_encoder_fold_fwd", _p(w), _p(b), _p(gamma), _p(beta), _p(moments), _p(rm), _p(rv),
+              _p(nbt) if moments is not None else None, momentum, eps, _p(enc_w), _p(enc_b), h, _stream())
+        training = moments is not None
+        # eval-mode backward reads the (then unchanging) running statistics; train mode reads the moments
+        ctx.save_for_backward(w, b, gamma, moments, None if training else rm, None if training else rv)
+        ctx.eps = eps
+        return enc_w, enc_b
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g_enc_w, g_enc_b):
+        w, b, gamma, moments, rm, rv = ctx.saved_tensors
+        h = w.shape[0]
+        gw = torch.empty_like(w)
+        gb = torch.empty_like(b) if b is not None else None
+        gg = torch.empty_like(gamma)
+        gbeta = torch.empty_like(gamma)
+        _call("b200_encoder_fold_bwd", _p(w), _p(b), _p(gamma), _p(moments), _p(rm), _p(rv), ctx.eps,
+              _p(_f32c(g_enc_w)), _p(_f32c(g_enc_b)), _p(gw), _p(gb), _p(gg), _p(gbeta), h, _stream())
+        return gw, gb, gg, gbeta, None, None, None, None, None, None
+
+
+def encoder_fold(lin: torch.nn.Linear, bn: torch.nn.BatchNorm1d, moments: Optional[Tensor], num_edges: int,
+                 training: bool) -> Tuple[Tensor, Tensor]:
+    """(enc_w [h,7], enc_b [h]) of an LFA's mlp_encoder; see ``b200_encoder_fold_fwd`` in the C header."""
+    _need_cuda(lin.weight)
+    if training and num_edges <= 1:
+        raise ValueError(f"Expected more than 1 value per channel when training, got input size [{num_edges}, 10]")
+    return _EncoderFold.apply(lin.weight, lin.bias, bn.weight, bn.bias, moments if training else None,
+                              bn.running_mean, bn.running_var, bn.num_batches_tracked, float(bn.momentum),
+                              float(bn.eps))
 
 
 # ------------------------------------------------------------------ LocSE + attentive pooling
@@ -262,24 +330,26 @@ class _BNAct(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, y1, stats1, g1, b1, rm1, rv1, y2, stats2, g2, b2, rm2, rv2, slope, momentum, eps):
+    def forward(ctx, y1, stats1, g1, b1, rm1, rv1, nbt1, y2, stats2, g2, b2, rm2, rv2, nbt2, slope, momentum, eps):
         lib = _lib.load()
         n, c = y1.shape
         dev = y1.device
         training = stats1 is not None
 
-        def finalize(stats, g, b, rm, rv):
+        def finalize(stats, g, b, rm, rv, nbt):
             buf = torch.empty((4, c), dtype=torch.float32, device=dev)  # scale, shift, mean, invstd
-            _call("b200_bn_finalize", _p(stats), n, _p(g), _p(b), _p(rm), _p(rv), momentum, eps,
+            _call("b200_bn_finalize", _p(stats), n, _p(g), _p(b), _p(rm), _p(rv), _p(nbt), momentum, eps,
                                       _p(buf[0]), _p(buf[1]), _p(buf[2]), _p(buf[3]), c, _stream())
             return buf
 
         g1, b1 = _f32c(g1), _f32c(b1)
-        aff1 = finalize(stats1, g1, b1, rm1, rv1)
+        y1 = _f32c(y1)
+        aff1 = finalize(stats1, g1, b1, rm1, rv1, nbt1)
         aff2 = None
         if y2 is not None:
             g2, b2 = _f32c(g2), _f32c(b2)
-            aff2 = finalize(stats2, g2, b2, rm2, rv2)
+            y2 = _f32c(y2)
+            aff2 = finalize(stats2, g2, b2, rm2, rv2, nbt2)
         out = torch.empty_like(y1)
         _call("b200_affine_act_fwd", _p(y1), _p(aff1[0]), _p(aff1[1]), _p(y2),
                                      _p(aff2[0]) if aff2 is not None else None,
@@ -314,7 +384,7 @@ class _BNAct(torch.autograd.Function):
         gg2 = gb2 = None
         if y2 is not None:
             gg2, gb2 = red2[c:].float(), red2[:c].float()
-        return (gy1, None, gg1, gb1, None, None, gy2, None, gg2, gb2, None, None, None, None, None)
+        return (gy1, None, gg1, gb1, None, None, None, gy2, None, gg2, gb2, None, None, None, None, None, None)
 
 
 def bn_act(y: Tensor, stats: Optional[Tensor], bn: torch.nn.BatchNorm1d, slope: float,
@@ -332,14 +402,9 @@ def bn_act(y: Tensor, stats: Optional[Tensor], bn: torch.nn.BatchNorm1d, slope: 
         return m.running_mean, m.running_var
 
     rm1, rv1 = buffers(bn)
-    args2 = (None, None, None, None, None, None)
+    args2 = (None, None, None, None, None, None, None)
     if y2 is not None:
         rm2, rv2 = buffers(bn2)
-        args2 = (y2, stats2, bn2.weight, bn2.bias, rm2, rv2)
-    out = _BNAct.apply(y, stats, bn.weight, bn.bias, rm1, rv1, *args2, float(slope), float(bn.momentum), float(bn.eps))
-    if training:
-        with torch.no_grad():
-            bn.num_batches_tracked += 1
-            if bn2 is not None:
-                bn2.num_batches_tracked += 1
-    return out
+        args2 = (y2, stats2, bn2.weight, bn2.bias, rm2, rv2, bn2.num_batches_tracked)
+    return _BNAct.apply(y, stats, bn.weight, bn.bias, rm1, rv1, bn.num_batches_tracked, *args2, float(slope),
+                        float(bn.momentum), float(bn.eps))

@@ -65,7 +65,8 @@ class SharedMLP(nn.Module):
 
 def fold_encoder(enc: SharedMLP, moments: Optional[Tensor], num_edges: int, training: bool):
     """Fold ``mlp_encoder`` (Linear(10->h) + BatchNorm, pyg_randla_net.py:117,144) into an affine map
-    of ``q = (p_i, p_j, |p_j - p_i|)``.
+    of ``q = (p_i, p_j, |p_j - p_i|)``.  Plain-torch SPECIFICATION of ``ops.encoder_fold`` (the kernel
+    ``b200_encoder_fold_fwd/bwd`` is what the network runs); kept for the tests that pin the algebra.
 
     The reference feeds ``r = [p_i, p_j, p_j - p_i, dist]`` (:143): ``W r = W~ q`` with
     ``W~ = [W_a - W_c, W_b + W_c, w_d]``.  In training the BatchNorm statistics over all E edges are
@@ -111,8 +112,21 @@ class _Level:
         self.max_n = max(sizes) if sizes else 0
         self.ptr = ptr_dev if ptr_dev is not None else torch.tensor(ptr_host, dtype=torch.int64, device=device)
 
+        self._decim_cache = None
+
     def num_edges(self, k: int) -> int:
         return sum(n * min(k, n) for n in self.sizes)
+
+    def decimation_tables(self, new_ptr_host: Sequence[int]):
+        """(cloud id << 32 per point, positions kept per cloud) for :func:`fused_decimation_indices`."""
+        if self._decim_cache is None:
+            dev = self.ptr.device
+            sizes = torch.tensor(self.sizes, dtype=torch.int64)
+            cloud = torch.repeat_interleave(torch.arange(len(self.sizes), dtype=torch.int64), sizes)
+            take = torch.cat([torch.arange(self.ptr_host[b], self.ptr_host[b] + (new_ptr_host[b + 1] - new_ptr_host[b]),
+                                           dtype=torch.int64) for b in range(len(self.sizes))])
+            self._decim_cache = ((cloud << 32).to(dev), take.to(dev))
+        return self._decim_cache
 
 
 class LocalFeatureAggregation(nn.Module):
@@ -125,7 +139,8 @@ class LocalFeatureAggregation(nn.Module):
         self.mlp_post_attention = SharedMLP([channels, channels])
 
     def forward(self, x: Tensor, pos: Tensor, nbr: Tensor, moments: Optional[Tensor], num_edges: int) -> Tensor:
-        enc_w, enc_b = fold_encoder(self.mlp_encoder, moments, num_edges, self.training)
+        enc = self.mlp_encoder
+        enc_w, enc_b = ops.encoder_fold(enc.lins[0], enc.norms[0].module, moments, num_edges, self.training)
         pooled = ops.lfa_attentive_pool(x, pos, nbr, enc_w, enc_b, self.mlp_attention.lins[0].weight)
         return self.mlp_post_attention(pooled)
 
@@ -197,6 +212,18 @@ def decimation_indices(ptr_host: Sequence[int], decimation_factor: Number, devic
     return torch.cat(parts, dim=0), new_ptr
 
 
+def fused_decimation_indices(level: "_Level", new_ptr_host: Sequence[int]) -> Tensor:
+    """Same distribution as :func:`decimation_indices` -- per cloud, a uniformly random ORDERED subset of
+    ``max(1, n // decimation)`` points -- drawn for ALL clouds at once: one random key per point, one sort of
+    (cloud id, key), one gather of each cloud's leading positions.  ~4 launches per level instead of
+    ~7 per cloud (the reference's Python loop); the random stream differs from the
+    reference's per-cloud ``randperm`` calls, the statistics do not."""
+    shift, take = level.decimation_tables(new_ptr_host)
+    keys = torch.randint(0, 2 ** 31 - 1, (level.n,), dtype=torch.int64, device=shift.device)
+    order = torch.argsort(keys + shift)
+    return order[take]
+
+
 class FPModule(nn.Module):
     """pyg_randla_net.py:241-253: k-NN (k=1) inverse-distance upsampling + skip concat + SharedMLP."""
 
@@ -206,7 +233,8 @@ class FPModule(nn.Module):
         self.nn = net
 
     def forward(self, x: Tensor, pos: Tensor, level: _Level, x_skip: Tensor, pos_skip: Tensor, level_skip: _Level) -> Tensor:
-        nbr, dist2 = ops.knn(pos, level.ptr, pos_skip, level_skip.ptr, self.k, level_skip.max_n, kt=self.k)
+        nbr, dist2 = ops.knn(pos, level.ptr, pos_skip, level_skip.ptr, self.k, level_skip.max_n, kt=self.k,
+                             max_points_per_cloud=level.max_n)
         xi = ops.knn_interpolate_from_table(x, nbr, dist2, self.k)  # :250
         return self.nn(xi, x_skip)  # cat + SharedMLP (:251-252) without materialising the cat
 
@@ -239,30 +267,60 @@ class B200RandLANet(nn.Module):
         self.mlp_classif = SharedMLP([d_bottleneck, 64, 32], dropout=[0.0, 0.5])
         self.fc_classif = nn.Linear(32, num_classes)
 
+        # host-side caches / static-shape hooks (see myria3d_b200.graphed.GraphedTrainStep)
+        self._level_cache: Dict[tuple, List[_Level]] = {}
+        self.static_ptr_host: Optional[List[int]] = None  # skips the ptr device->host read when set
+        # "reference": per-cloud torch.randperm calls exactly like pyg_randla_net.py:219-229 (same subsets as
+        # the reference under a fixed seed on the same device); "fused": one batched draw per level.
+        self.decimation_rng = "reference"
         # parity harness hooks (never set in production)
         self.injected_decimation_idx: Optional[List[Tensor]] = None
         self.last_decimation_idx: List[Tensor] = []
         self.keep_stages = False
         self.stages: Dict[str, Tensor] = {}
 
-    def _decimate(self, tensors, level: _Level, lvl_idx: int):
+    def levels_for(self, ptr_host: Sequence[int], device: torch.device) -> List["_Level"]:
+        """The 5 resolution levels (ptr on host and device) of a batch layout.  Cloud sizes after each
+        decimation are deterministic (max(1, n // decimation)), so they are computed once per layout
+        and cached: no per-step host->device copies, and a static layout can be CUDA-graph captured."""
+        key = (tuple(int(v) for v in ptr_host), str(device))
+        levels = self._level_cache.get(key)
+        if levels is None:
+            levels = [_Level(list(key[0]), device)]
+            for _ in range(4):
+                levels.append(_Level(decimation_sizes(levels[-1].ptr_host, self.decimation), device))
+            if len(self._level_cache) >= 16:
+                self._level_cache.pop(next(iter(self._level_cache)))
+            self._level_cache[key] = levels
+        return levels
+
+    def draw_decimation(self, levels: List["_Level"], lvl_idx: int) -> Tensor:
+        if self.decimation_rng == "fused":
+            return fused_decimation_indices(levels[lvl_idx], levels[lvl_idx + 1].ptr_host)
+        return decimation_indices(levels[lvl_idx].ptr_host, self.decimation, levels[lvl_idx].ptr.device)[0]
+
+    def _decimate(self, tensors, levels: List["_Level"], lvl_idx: int):
         """decimate() of pyg_randla_net.py:234-238 (x rows through the gather kernel; pos rows too)."""
         if self.injected_decimation_idx is not None:
             idx = self.injected_decimation_idx[lvl_idx].to(device=tensors[0].device, dtype=torch.int64)
-            new_ptr = decimation_sizes(level.ptr_host, self.decimation)
         else:
-            idx, new_ptr = decimation_indices(level.ptr_host, self.decimation, tensors[0].device)
+            idx = self.draw_decimation(levels, lvl_idx)
         self.last_decimation_idx.append(idx)
-        out = tuple(ops.gather_rows(t, idx) for t in tensors)
-        return out, _Level(new_ptr, tensors[0].device)
+        return tuple(ops.gather_rows(t, idx) for t in tensors)
 
     def forward(self, x: Optional[Tensor], pos: Tensor, batch: Optional[Tensor], ptr: Tensor) -> Tensor:
         if not pos.is_cuda:
             raise RuntimeError("B200RandLANet runs on a CUDA (B200) device only; there is no CPU fallback")
         x = x if x is not None else pos  # :56
         pos = pos.float().contiguous()
-        ptr_host = [int(v) for v in ptr.tolist()]  # the only device->host sync of the forward
-        lvl0 = _Level(ptr_host, pos.device, ptr.to(device=pos.device, dtype=torch.int64).contiguous())
+        if self.decimation < 1:
+            decimation_sizes([0, 1], self.decimation)  # raises the reference's ValueError
+        if self.static_ptr_host is not None:
+            ptr_host = self.static_ptr_host
+        else:
+            ptr_host = [int(v) for v in ptr.tolist()]  # the only device->host sync of the forward
+        levels = self.levels_for(ptr_host, pos.device)
+        lvl0, lvl1, lvl2, lvl3, lvl4 = levels
         self.last_decimation_idx = []
         self.stages = {}
 
@@ -273,16 +331,16 @@ class B200RandLANet(nn.Module):
         h0 = ops.linear(x, self.fc0.weight, self.fc0.bias)  # fc0 (:58)
         b1 = self.block1(h0, pos, lvl0)
         keep("b1", b1)
-        (b1d, pos1), lvl1 = self._decimate((b1, pos), lvl0, 0)  # :59
+        b1d, pos1 = self._decimate((b1, pos), levels, 0)  # :59
         b2 = self.block2(b1d, pos1, lvl1)
         keep("b2", b2)
-        (b2d, pos2), lvl2 = self._decimate((b2, pos1), lvl1, 1)  # :62
+        b2d, pos2 = self._decimate((b2, pos1), levels, 1)  # :62
         b3 = self.block3(b2d, pos2, lvl2)
         keep("b3", b3)
-        (b3d, pos3), lvl3 = self._decimate((b3, pos2), lvl2, 2)  # :65
+        b3d, pos3 = self._decimate((b3, pos2), levels, 2)  # :65
         b4 = self.block4(b3d, pos3, lvl3)
         keep("b4", b4)
-        (b4d, pos4), lvl4 = self._decimate((b4, pos3), lvl3, 3)  # :68
+        b4d, pos4 = self._decimate((b4, pos3), levels, 3)  # :68
 
         summit = self.mlp_summit(b4d)  # :70
         keep("summit", summit)

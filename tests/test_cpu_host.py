@@ -21,7 +21,7 @@ def test_library_exports_every_header_symbol(lib):
     assert declared == set(_lib.EXPORTED_SYMBOLS), declared ^ set(_lib.EXPORTED_SYMBOLS)
     for name in declared:
         assert hasattr(lib, name), f"{name} not exported by libb200randla.so"
-    assert lib.b200_abi_version() == 1 == int(re.search(r"#define B200_ABI_VERSION (\d+)", header).group(1))
+    assert lib.b200_abi_version() == 2 == int(re.search(r"#define B200_ABI_VERSION (\d+)", header).group(1))
     assert lib.b200_last_error() == b"" or isinstance(lib.b200_last_error(), bytes)
     assert lib.b200_launch_count() >= 0
 
@@ -142,3 +142,27 @@ def test_state_dict_keys_match_oracle():
     b = O.OracleRandLANet(9, 7).state_dict()
     assert list(a.keys()) == list(b.keys())
     assert all(a[k].shape == b[k].shape and a[k].dtype == b[k].dtype for k in a)
+
+
+def test_fused_decimation_is_a_valid_draw():
+    """One batched draw: right counts per cloud, no duplicates, indices stay inside their cloud, random order."""
+    from myria3d_b200.randla_net import _Level, decimation_sizes, fused_decimation_indices
+
+    ptr = [0, 1000, 1003, 1004, 3004]
+    lvl = _Level(ptr, torch.device("cpu"))
+    new_ptr = decimation_sizes(ptr, 4)
+    torch.manual_seed(0)
+    idx = fused_decimation_indices(lvl, new_ptr)
+    assert idx.numel() == new_ptr[-1] == 250 + 1 + 1 + 500
+    for b in range(4):
+        part = idx[new_ptr[b]:new_ptr[b + 1]]
+        assert ((part >= ptr[b]) & (part < ptr[b + 1])).all()
+        assert part.unique().numel() == part.numel()
+    assert not torch.equal(idx[:250], idx[:250].sort().values)  # not sorted: order is random too
+    idx2 = fused_decimation_indices(lvl, new_ptr)
+    assert not torch.equal(idx, idx2)
+    # uniformity: every point of cloud 0 is kept ~ 1/4 of the time
+    hits = torch.zeros(1000)
+    for _ in range(200):
+        hits[fused_decimation_indices(lvl, new_ptr)[:250]] += 1
+    assert abs(float(hits.mean()) - 50.0) < 1e-6 and float(hits.std()) < 9.0

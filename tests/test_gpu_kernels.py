@@ -68,6 +68,48 @@ def test_knn_large_property(lib):
     assert torch.equal(nbr, ref)
 
 
+@pytest.mark.parametrize("k", [16, 1, 10, 32])
+@pytest.mark.parametrize("dist", ["cube", "lidar", "line", "duplicates", "lattice"])
+def test_knn_grid_equals_bruteforce(lib, k, dist):
+    """Bucket-grid search == tiled brute force == oracle, bit for bit (indices and distances), on point
+    distributions that stress the pruning: isotropic cube, flat Lidar tile, collinear points, clouds made of
+    repeated points (ties decided by index), exact lattice (many equal distances)."""
+    from myria3d_b200 import ops
+
+    g = torch.Generator().manual_seed(hash((k, dist)) % 1000)
+    sizes = [3000, 5, 1, 777, 1500]
+    n = sum(sizes)
+    if dist == "cube":
+        pos = torch.rand(n, 3, generator=g)
+    elif dist == "lidar":
+        pos = O.synthetic_batch(sizes, seed=5)[1]
+    elif dist == "line":
+        t = torch.rand(n, 1, generator=g)
+        pos = torch.cat([t * 3.0 - 1.0, t * 0.5 + 2.0, torch.zeros(n, 1)], 1)
+    elif dist == "duplicates":
+        base = torch.rand(40, 3, generator=g)
+        pos = base[torch.randint(0, 40, (n,), generator=g)]
+    else:
+        ij = torch.randint(0, 24, (n, 3), generator=g).float()
+        pos = ij * 0.125
+    ptr = torch.tensor(ptr_of(sizes))
+    pd, pt = pos.to(DEV), ptr.to(DEV)
+    kt = k
+    a_n, a_d = ops.knn(pd, pt, pd, pt, k, max(sizes), kt=kt, algo="brute")
+    b_n, b_d = ops.knn(pd, pt, pd, pt, k, max(sizes), kt=kt, algo="grid")
+    assert torch.equal(a_n, b_n), f"{int((a_n != b_n).sum())} index mismatches"
+    assert torch.equal(a_d, b_d)
+    ref, _ = O.knn_bruteforce(pos, ptr.tolist(), pos, ptr.tolist(), k)
+    assert torch.equal(b_n.cpu().long(), ref)
+    # queries != candidates, queries partly outside the candidates' bounding box
+    sy = [900, 40, 3, 10, 2000]
+    qpos = (torch.rand(sum(sy), 3, generator=g) * 1.6 - 0.3).to(DEV)
+    qptr = torch.tensor(ptr_of(sy), device=DEV)
+    c_n, c_d = ops.knn(pd, pt, qpos, qptr, k, max(sy), max_points_per_cloud=max(sizes), algo="brute")
+    d_n, d_d = ops.knn(pd, pt, qpos, qptr, k, max(sy), max_points_per_cloud=max(sizes), algo="grid")
+    assert torch.equal(c_n, d_n) and torch.equal(c_d, d_d)
+
+
 # ---------------------------------------------------------------------------------- edge moments
 def test_edge_moments(lib):
     from myria3d_b200 import ops
@@ -85,6 +127,36 @@ def test_edge_moments(lib):
     out = ops.edge_moments(pos.to(DEV), nbr.int().to(DEV)).cpu()
     assert out[0].item() == q.shape[0]
     assert_close(out, ref, atol=1e-9, rtol=1e-8, what="edge moments")
+
+
+@pytest.mark.parametrize("training", [True, False])
+def test_encoder_fold_kernel_vs_torch_spec(lib, training):
+    """b200_encoder_fold_fwd/bwd == the differentiable torch specification (randla_net.fold_encoder)."""
+    import copy
+
+    from myria3d_b200 import ops
+    from myria3d_b200.randla_net import SharedMLP, fold_encoder
+
+    g = torch.Generator().manual_seed(3)
+    q = torch.rand(5000, 7, generator=g).double()
+    moments = torch.cat([torch.tensor([5000.0], dtype=torch.float64), q.sum(0), (q.t() @ q).flatten()]).to(DEV)
+    enc = SharedMLP([10, 32])
+    bn = enc.norms[0].module
+    bn.weight.data.uniform_(0.5, 1.5, generator=g), bn.bias.data.uniform_(-0.5, 0.5, generator=g)
+    bn.running_mean.uniform_(-0.3, 0.3, generator=g), bn.running_var.uniform_(0.5, 1.5, generator=g)
+    enc.to(DEV).train(training)
+    enc2 = copy.deepcopy(enc)
+    w_ref, b_ref = fold_encoder(enc, moments, 5000, training)
+    w, b = ops.encoder_fold(enc2.lins[0], enc2.norms[0].module, moments, 5000, training)
+    assert_close(w, w_ref, atol=1e-6, rtol=1e-5, what="enc_w")
+    assert_close(b, b_ref, atol=1e-6, rtol=1e-5, what="enc_b")
+    gw, gb = torch.randn(32, 7, generator=g).to(DEV), torch.randn(32, generator=g).to(DEV)
+    (w_ref * gw).sum().add((b_ref * gb).sum()).backward()
+    (w * gw).sum().add((b * gb).sum()).backward()
+    for (n1, p1), (_, p2) in zip(enc2.named_parameters(), enc.named_parameters()):
+        assert_close(p1.grad, p2.grad, atol=1e-5, rtol=1e-4, what=f"fold grad {n1}")
+    for (n1, b1), (_, b2) in zip(enc2.named_buffers(), enc.named_buffers()):
+        assert_close(b1, b2, atol=1e-6, rtol=1e-5, what=f"fold buffer {n1}")
 
 
 # ------------------------------------------------------------------------- LFA forward / backward
