@@ -134,7 +134,7 @@ def algorithmic_bytes(name: str, a):
         n, c, kt = a
         return n * (6 * c + 12 + 4 * kt)
     if name == "b200_lfa_bwd":
-        n, c, kt = a
+        _ws, n, c, kt = a
         return n * (8 * c + 12 + 4 * kt)
     if name == "b200_knn":
         nx, ny, _clouds, _maxq, k, kt = a

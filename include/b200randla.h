@@ -120,11 +120,16 @@ int b200_lfa_fwd(const float* x, const float* pos, const int32_t* nbr,
  * grad_att_w are ACCUMULATED into (atomics): the caller zero-fills them.
  *   att_w   fp32 [c, c]  mlp_attention.lins.0.weight as stored ([out, in])
  *   grad_att_w fp32 [c, c] in the same [out, in] layout
+ *   workspace: b200_lfa_bwd_workspace_bytes(n, c, kt) bytes of scratch (16-byte aligned; 0 bytes / NULL for
+ *   c <= 32).  For c >= 64 the per-edge softmax gradients and features are streamed there and the
+ *   attention-weight gradient is reduced by a split-K GEMM instead of per-tile atomics.
  */
+int64_t b200_lfa_bwd_workspace_bytes(int64_t n, int32_t c, int32_t kt);
 int b200_lfa_bwd(const float* x, const float* pos, const int32_t* nbr,
                  const float* enc_w, const float* enc_b, const float* att_wt, const float* att_w,
                  const float* grad_out,
                  float* grad_x, float* grad_enc_w, float* grad_enc_b, float* grad_att_w,
+                 void* workspace, int64_t workspace_bytes,
                  int64_t n, int32_t c, int32_t kt, void* stream);
 
 /* ------------------------------------------------------- index / scatter kernels -------
@@ -162,9 +167,12 @@ int b200_knn_interp_bwd(const float* grad_y, int64_t ld_grad, const int32_t* nbr
  *   a1 fp32 [n, c1] (row stride ld1), a2 fp32 [n, c2] (row stride ld2) or NULL with c2 = 0:
  *   the K dimension is the concatenation (FPModule's torch.cat, pyg_randla_net.py:251).
  *   w fp32 [cout, c1+c2] row-major, bias fp32 [cout] or NULL.
- *   If colstats != NULL (fp64 [2*cout], pre-zeroed) the epilogue also accumulates
- *   sum_i y[i,ch] and sum_i y[i,ch]^2 for the BatchNorm that follows.
+ *   If colstats != NULL the epilogue also produces, for the BatchNorm that follows, per-ROW-TILE partial
+ *   sums: colstats fp64 [P, 2*cout] with P = b200_linear_fwd_num_stat_partials(n, c1, c2, cout); row p holds
+ *   (sum_i y[i,ch], sum_i y[i,ch]^2) over the rows of tile p.  Rows are WRITTEN (no zero-fill, no atomics);
+ *   b200_bn_finalize adds them up.
  */
+int64_t b200_linear_fwd_num_stat_partials(int64_t n, int32_t c1, int32_t c2, int32_t cout);
 int b200_linear_fwd(const float* a1, int64_t ld1, int32_t c1, const float* a2, int64_t ld2, int32_t c2,
                     const float* w, const float* bias, float* y, int64_t n, int32_t cout,
                     double* colstats, void* stream);
@@ -177,13 +185,13 @@ int b200_linear_bwd_weight(const float* grad_y, const float* a1, int64_t ld1, in
                            const float* a2, int64_t ld2, int32_t c2,
                            float* grad_w, float* grad_bias, int64_t n, int32_t cout, void* stream);
 
-/* BatchNorm statistics -> per-channel affine.  colstats fp64 [2*c] = (sum, sum of squares)
- * over `count` rows.  Writes scale = gamma*invstd, shift = beta - mean*scale, and
+/* BatchNorm statistics -> per-channel affine.  colstats fp64 [num_partials, 2*c] = partial (sum, sum of
+ * squares) rows that add up to the statistics over `count` rows.  Writes scale = gamma*invstd, shift = beta - mean*scale, and
  * mean / invstd (saved for backward).  If running_mean != NULL updates the running
  * statistics in place: r = (1-momentum) r + momentum * stat (unbiased variance).
  * and increments *num_batches_tracked (int64, may be NULL).
  * With colstats == NULL (eval mode) uses the running statistics instead. */
-int b200_bn_finalize(const double* colstats, int64_t count, const float* gamma, const float* beta,
+int b200_bn_finalize(const double* colstats, int32_t num_partials, int64_t count, const float* gamma, const float* beta,
                      float* running_mean, float* running_var, int64_t* num_batches_tracked,
                      float momentum, float eps,
                      float* scale, float* shift, float* mean, float* invstd, int32_t c, void* stream);

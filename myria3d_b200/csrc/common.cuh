@@ -34,6 +34,9 @@ int num_sms();
     ::b200::count_launch();                                       \
   } while (0)
 
+// out[m][k] += sum_i a[i][m] * b[i][k]  (a: [n, ca], b: [n, cb], out: [ca, cb]; split-K over n, atomics)
+int accumulate_at_b(const float* a, int ca, const float* b, int cb, float* out, int64_t n, cudaStream_t st);
+
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 constexpr float kLReluSlope = 0.2f;  // pyg_randla_net.py:92

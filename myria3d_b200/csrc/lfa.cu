@@ -287,7 +287,7 @@ __device__ __forceinline__ void centre_gemm(float (&acc)[Cfg::KT][Cfg::CW], cons
 // forward
 // ------------------------------------------------------------------------------------------
 template <class Cfg>
-__global__ void __launch_bounds__(Cfg::THREADS, 1)
+__global__ void __launch_bounds__(Cfg::THREADS, (Cfg::THREADS <= 128 ? 3 : 1))
 lfa_fwd_kernel(const float* __restrict__ x, const float* __restrict__ pos, const int32_t* __restrict__ nbr,
                const float* __restrict__ enc_w, const float* __restrict__ enc_b,
                const float* __restrict__ att_wt, float* __restrict__ out, int64_t n, int64_t ntiles) {
@@ -351,6 +351,13 @@ lfa_fwd_kernel(const float* __restrict__ x, const float* __restrict__ pos, const
 // ------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------
+// Two flavours of the attention-weight gradient dW[n][m] = sum_e DA[e][n] F[e][m]:
+//   SPLIT_DW = false (C <= 32, millions of edges): 4x4 register blocks per thread, accumulated over all
+//              the tiles a persistent CTA visits, reduced once at the end (no per-tile atomics);
+//   SPLIT_DW = true  (C >= 64, deep levels, few edges): the tile's DA and F rows are streamed to a
+//              caller-provided workspace ([E, C] each) and a split-K GEMM (pointwise.cu) reduces them; the
+//              fused kernel then needs neither C*C accumulators nor C*C atomics per tile, so it can use
+//              small tiles and several CTAs per SM.
 template <class Cfg>
 struct LfaBwdPlan {
   static constexpr int C = Cfg::C, THREADS = Cfg::THREADS;
@@ -358,21 +365,22 @@ struct LfaBwdPlan {
   static constexpr int NBLOCKS = NB4 * NB4;
   static constexpr int SLICES = (NBLOCKS >= THREADS) ? 1 : (THREADS / NBLOCKS);  // edge slices per block
   static constexpr int PASSES = (NBLOCKS >= THREADS) ? (NBLOCKS / THREADS) : 1;
-  static constexpr bool PERSIST = PASSES <= 2;       // keep dW partials in registers across tiles
-  static_assert(SLICES <= 32 && (SLICES & (SLICES - 1)) == 0, "slices must be a power of two <= 32");
-  static_assert(NBLOCKS >= THREADS ? (NBLOCKS % THREADS == 0) : (THREADS % NBLOCKS == 0), "GEMM3 mapping");
+  static constexpr bool GE_IN_REGS = (C <= 32);      // encoder-gradient partials live in registers
 };
 
-template <class Cfg>
-__global__ void __launch_bounds__(Cfg::THREADS, 1)
+template <class Cfg, bool SPLIT_DW>
+__global__ void __launch_bounds__(Cfg::THREADS, (Cfg::THREADS <= 128 ? 3 : 1))
 lfa_bwd_kernel(const float* __restrict__ x, const float* __restrict__ pos, const int32_t* __restrict__ nbr,
                const float* __restrict__ enc_w, const float* __restrict__ enc_b,
                const float* __restrict__ att_wt, const float* __restrict__ att_w,
                const float* __restrict__ grad_out, float* __restrict__ grad_x, float* __restrict__ grad_enc_w,
-               float* __restrict__ grad_enc_b, float* __restrict__ grad_att_w, int64_t n, int64_t ntiles) {
+               float* __restrict__ grad_enc_b, float* __restrict__ grad_att_w, float* __restrict__ da_out,
+               float* __restrict__ f_out, int64_t n, int64_t ntiles) {
   constexpr int C = Cfg::C, KT = Cfg::KT, CW = Cfg::CW, TC = Cfg::TC, TPC = Cfg::TPC, H = Cfg::H;
   constexpr int THREADS = Cfg::THREADS, EDGES = Cfg::EDGES, CSTRIDE = Cfg::CSTRIDE;
   using Plan = LfaBwdPlan<Cfg>;
+  static_assert(SPLIT_DW || Plan::PASSES <= 2, "register dW accumulation needs <= 2 passes");
+  static_assert(SPLIT_DW || (Plan::SLICES <= 32 && (Plan::SLICES & (Plan::SLICES - 1)) == 0), "slices: power of two <= 32");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* F = reinterpret_cast<float*>(smem_raw);
   float* DA = F + Cfg::TILE_FLOATS;
@@ -386,11 +394,18 @@ lfa_bwd_kernel(const float* __restrict__ x, const float* __restrict__ pos, const
 
   for (int t = tid; t < H * 8; t += THREADS) GE[t] = 0.f;
 
-  float dw[Plan::PERSIST ? Plan::PASSES : 1][16];
+  constexpr int DWP = SPLIT_DW ? 1 : Plan::PASSES;
+  float dw[DWP][16];
 #pragma unroll
-  for (int p = 0; p < (Plan::PERSIST ? Plan::PASSES : 1); ++p)
+  for (int p = 0; p < DWP; ++p)
 #pragma unroll
     for (int t = 0; t < 16; ++t) dw[p][t] = 0.f;
+  constexpr int GEW = Plan::GE_IN_REGS ? CW : 1;
+  float ge_reg[GEW][8];
+#pragma unroll
+  for (int cw = 0; cw < GEW; ++cw)
+#pragma unroll
+    for (int t = 0; t < 8; ++t) ge_reg[cw][t] = 0.f;
 
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int64_t tile_base = tile * TC;
@@ -442,10 +457,9 @@ lfa_bwd_kernel(const float* __restrict__ x, const float* __restrict__ pos, const
       }
 #pragma unroll
       for (int k = 0; k < KT; ++k) {
-        float da[CW];
+        float da[CW], f[CW];
+        load_vec<CW>(f, Fg + k * C + col0);  // zeros for invalid edges
         if (k < deg) {
-          float f[CW];
-          load_vec<CW>(f, Fg + k * C + col0);
 #pragma unroll
           for (int cw = 0; cw < CW; ++cw) {
             const float sg = acc[k][cw] * inv[cw] * go[cw];
@@ -460,6 +474,13 @@ lfa_bwd_kernel(const float* __restrict__ x, const float* __restrict__ pos, const
           }
         }
         store_vec<CW>(DAg + k * C + col0, da);
+        if constexpr (SPLIT_DW) {
+          if (i < n) {  // stream the edge rows out for the split-K dW GEMM
+            const int64_t row = (i * KT + k) * C + col0;
+            store_vec<CW>(da_out + row, da);
+            store_vec<CW>(f_out + row, f);
+          }
+        }
       }
     }
     __syncthreads();
@@ -496,48 +517,43 @@ lfa_bwd_kernel(const float* __restrict__ x, const float* __restrict__ pos, const
             gw[7] += dz;
           }
         gw[0] = gw[7] * p.x, gw[1] = gw[7] * p.y, gw[2] = gw[7] * p.z;
-        float* ge = GE + (col0 - H + cw) * 8;
+        if constexpr (Plan::GE_IN_REGS) {
 #pragma unroll
-        for (int t = 0; t < 8; ++t) atomicAdd(ge + t, gw[t]);
+          for (int t = 0; t < 8; ++t) ge_reg[cw][t] += gw[t];
+        } else {
+          float* ge = GE + (col0 - H + cw) * 8;
+#pragma unroll
+          for (int t = 0; t < 8; ++t) atomicAdd(ge + t, gw[t]);
+        }
       }
     }
 
-    // GEMM3: dW[n][m] += sum_e DA[e][n] F[e][m], 4x4 register blocks
+    if constexpr (!SPLIT_DW) {
+      // GEMM3: dW[n][m] += sum_e DA[e][n] F[e][m], 4x4 register blocks carried across tiles
 #pragma unroll
-    for (int pass = 0; pass < Plan::PASSES; ++pass) {
-      const int ob = (Plan::SLICES > 1) ? (tid / Plan::SLICES) : (pass * THREADS + tid);
-      const int es = (Plan::SLICES > 1) ? (tid % Plan::SLICES) : 0;
-      const int nb = ob / Plan::NB4, mb = ob % Plan::NB4;
-      float part[16];
-#pragma unroll
-      for (int t = 0; t < 16; ++t) part[t] = Plan::PERSIST ? dw[Plan::PERSIST ? pass : 0][t] : 0.f;
+      for (int pass = 0; pass < Plan::PASSES; ++pass) {
+        const int ob = (Plan::SLICES > 1) ? (tid / Plan::SLICES) : (pass * THREADS + tid);
+        const int es = (Plan::SLICES > 1) ? (tid % Plan::SLICES) : 0;
+        const int nb = ob / Plan::NB4, mb = ob % Plan::NB4;
 #pragma unroll 4
-      for (int e = es; e < EDGES; e += Plan::SLICES) {
-        const int off = (e / KT) * CSTRIDE + (e % KT) * C;
-        const float4 a = *reinterpret_cast<const float4*>(DA + off + nb * 4);
-        const float4 b = *reinterpret_cast<const float4*>(F + off + mb * 4);
-        const float av[4] = {a.x, a.y, a.z, a.w};
-        const float bv[4] = {b.x, b.y, b.z, b.w};
+        for (int e = es; e < EDGES; e += Plan::SLICES) {
+          const int off = (e / KT) * CSTRIDE + (e % KT) * C;
+          const float4 a = *reinterpret_cast<const float4*>(DA + off + nb * 4);
+          const float4 b = *reinterpret_cast<const float4*>(F + off + mb * 4);
+          const float av[4] = {a.x, a.y, a.z, a.w};
+          const float bv[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-        for (int r = 0; r < 4; ++r)
+          for (int r = 0; r < 4; ++r)
 #pragma unroll
-          for (int s = 0; s < 4; ++s) part[r * 4 + s] = fmaf(av[r], bv[s], part[r * 4 + s]);
-      }
-      if constexpr (Plan::PERSIST) {
-#pragma unroll
-        for (int t = 0; t < 16; ++t) dw[pass][t] = part[t];
-      } else {
-#pragma unroll
-        for (int r = 0; r < 4; ++r)
-          atomicAdd(reinterpret_cast<float4*>(grad_att_w + (int64_t)(nb * 4 + r) * C + mb * 4),
-                    make_float4(part[r * 4 + 0], part[r * 4 + 1], part[r * 4 + 2], part[r * 4 + 3]));
+            for (int s = 0; s < 4; ++s) dw[pass][r * 4 + s] = fmaf(av[r], bv[s], dw[pass][r * 4 + s]);
+        }
       }
     }
     __syncthreads();  // tile buffers are rebuilt next iteration
   }
 
   // flush the per-CTA partial gradients
-  if constexpr (Plan::PERSIST) {
+  if constexpr (!SPLIT_DW) {
 #pragma unroll
     for (int pass = 0; pass < Plan::PASSES; ++pass) {
       const int ob = (Plan::SLICES > 1) ? (tid / Plan::SLICES) : (pass * THREADS + tid);
@@ -556,6 +572,14 @@ lfa_bwd_kernel(const float* __restrict__ x, const float* __restrict__ pos, const
           atomicAdd(reinterpret_cast<float4*>(grad_att_w + (int64_t)(nb * 4 + r) * C + mb * 4),
                     make_float4(dw[pass][r * 4 + 0], dw[pass][r * 4 + 1], dw[pass][r * 4 + 2], dw[pass][r * 4 + 3]));
       }
+    }
+  }
+  if constexpr (Plan::GE_IN_REGS) {
+    if (col0 >= H) {
+#pragma unroll
+      for (int cw = 0; cw < CW; ++cw)
+#pragma unroll
+        for (int t = 0; t < 8; ++t) atomicAdd(GE + (col0 - H + cw) * 8 + t, ge_reg[cw][t]);
     }
   }
   __syncthreads();
@@ -607,18 +631,23 @@ static int launch_lfa_fwd(const float* x, const float* pos, const int32_t* nbr, 
   return B200_OK;
 }
 
-template <class Cfg>
+template <class Cfg, bool SPLIT_DW>
 static int launch_lfa_bwd(const float* x, const float* pos, const int32_t* nbr, const float* enc_w,
                           const float* enc_b, const float* att_wt, const float* att_w, const float* go, float* gx,
-                          float* gew, float* geb, float* gaw, int64_t n, cudaStream_t st) {
+                          float* gew, float* geb, float* gaw, float* ws, int64_t n, cudaStream_t st) {
   const size_t smem = lfa_bwd_smem<Cfg>();
-  auto kern = lfa_bwd_kernel<Cfg>;
+  auto kern = lfa_bwd_kernel<Cfg, SPLIT_DW>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return cuda_fail(e, "lfa_bwd smem attribute");
   const int64_t ntiles = ceil_div(n, Cfg::TC);
   const int grid = persistent_grid(reinterpret_cast<const void*>(kern), Cfg::THREADS, smem, ntiles);
-  kern<<<grid, Cfg::THREADS, smem, st>>>(x, pos, nbr, enc_w, enc_b, att_wt, att_w, go, gx, gew, geb, gaw, n, ntiles);
+  float* da_out = SPLIT_DW ? ws : nullptr;
+  float* f_out = SPLIT_DW ? ws + n * Cfg::KT * Cfg::C : nullptr;
+  kern<<<grid, Cfg::THREADS, smem, st>>>(x, pos, nbr, enc_w, enc_b, att_wt, att_w, go, gx, gew, geb, gaw, da_out,
+                                         f_out, n, ntiles);
   B200_CHECK_LAUNCH("lfa_bwd_kernel");
+  if (SPLIT_DW)  // dW_att[n][m] += sum_e DA[e][n] F[e][m]: split-K GEMM over the streamed edge rows
+    return accumulate_at_b(da_out, Cfg::C, f_out, Cfg::C, gaw, n * Cfg::KT, st);
   return B200_OK;
 }
 
@@ -639,12 +668,16 @@ extern "C" int b200_edge_moments(const float* pos, const int32_t* nbr, int64_t n
 }
 
 // (C, KT) -> (CW, TC) tables; see the header comment for the reasoning.
+// X(C, KT, CW, TC[, SPLIT_DW]): THREADS = TC * C / CW.  Small tiles + CW = 4 keep registers near 128 and shared
+// memory near 33 KB (fwd) / 66 KB (bwd) so that 3-4 CTAs share an SM.
 #define B200_LFA_FWD_CASES(X) \
-  X(8, 16, 2, 32) X(16, 16, 4, 32) X(32, 16, 4, 16) X(64, 16, 8, 16) X(128, 16, 8, 8) X(256, 16, 8, 8) \
-  X(8, 32, 2, 32) X(16, 32, 4, 32) X(32, 32, 4, 16) X(64, 32, 4, 8) X(128, 32, 4, 4) X(256, 32, 4, 4)
-#define B200_LFA_BWD_CASES(X) \
-  X(8, 16, 2, 32) X(16, 16, 4, 32) X(32, 16, 4, 16) X(64, 16, 8, 16) X(128, 16, 8, 8) X(256, 16, 8, 4) \
+  X(8, 16, 2, 32) X(16, 16, 4, 32) X(32, 16, 4, 16) X(64, 16, 4, 8) X(128, 16, 4, 4) X(256, 16, 4, 2) \
   X(8, 32, 2, 32) X(16, 32, 4, 32) X(32, 32, 4, 16) X(64, 32, 4, 8) X(128, 32, 4, 4) X(256, 32, 4, 2)
+#define B200_LFA_BWD_CASES(X) \
+  X(8, 16, 2, 32, false) X(16, 16, 4, 32, false) X(32, 16, 4, 16, false) \
+  X(64, 16, 4, 8, true) X(128, 16, 4, 4, true) X(256, 16, 4, 2, true) \
+  X(8, 32, 2, 32, false) X(16, 32, 4, 32, false) X(32, 32, 4, 16, false) \
+  X(64, 32, 4, 4, true) X(128, 32, 4, 2, true) X(256, 32, 4, 2, true)
 
 extern "C" int b200_lfa_fwd(const float* x, const float* pos, const int32_t* nbr, const float* enc_w,
                             const float* enc_b, const float* att_wt, float* out, int64_t n, int32_t c, int32_t kt,
@@ -663,10 +696,15 @@ extern "C" int b200_lfa_fwd(const float* x, const float* pos, const int32_t* nbr
   return B200_E_UNSUPPORTED;
 }
 
+extern "C" int64_t b200_lfa_bwd_workspace_bytes(int64_t n, int32_t c, int32_t kt) {
+  if (n <= 0 || c < 64) return 0;
+  return 2 * n * (int64_t)kt * c * (int64_t)sizeof(float);
+}
+
 extern "C" int b200_lfa_bwd(const float* x, const float* pos, const int32_t* nbr, const float* enc_w,
                             const float* enc_b, const float* att_wt, const float* att_w, const float* grad_out,
-                            float* grad_x, float* grad_enc_w, float* grad_enc_b, float* grad_att_w, int64_t n,
-                            int32_t c, int32_t kt, void* stream) {
+                            float* grad_x, float* grad_enc_w, float* grad_enc_b, float* grad_att_w, void* workspace,
+                            int64_t workspace_bytes, int64_t n, int32_t c, int32_t kt, void* stream) {
   using namespace b200;
   B200_REQUIRE(x && pos && nbr && enc_w && enc_b && att_wt && att_w && grad_out && grad_x && grad_enc_w &&
                    grad_enc_b && grad_att_w,
@@ -675,11 +713,16 @@ extern "C" int b200_lfa_bwd(const float* x, const float* pos, const int32_t* nbr
                    ((uintptr_t)grad_out & 15) == 0 && ((uintptr_t)grad_x & 15) == 0 && ((uintptr_t)grad_att_w & 15) == 0,
                B200_E_INVALID, "b200_lfa_bwd: tensors must be 16-byte aligned");
   if (n <= 0) return B200_OK;
+  B200_REQUIRE(workspace_bytes >= b200_lfa_bwd_workspace_bytes(n, c, kt) && (workspace || workspace_bytes == 0) &&
+                   ((uintptr_t)workspace & 15) == 0,
+               B200_E_INVALID, "b200_lfa_bwd: workspace of %lld bytes needed (16-byte aligned)",
+               (long long)b200_lfa_bwd_workspace_bytes(n, c, kt));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-#define X(C_, KT_, CW_, TC_)                                                                                    \
-  if (c == C_ && kt == KT_)                                                                                     \
-    return launch_lfa_bwd<LfaCfg<C_, KT_, CW_, TC_>>(x, pos, nbr, enc_w, enc_b, att_wt, att_w, grad_out, grad_x, \
-                                                     grad_enc_w, grad_enc_b, grad_att_w, n, st);
+  float* ws = static_cast<float*>(workspace);
+#define X(C_, KT_, CW_, TC_, SPLIT_)                                                                       \
+  if (c == C_ && kt == KT_)                                                                                \
+    return launch_lfa_bwd<LfaCfg<C_, KT_, CW_, TC_>, SPLIT_>(x, pos, nbr, enc_w, enc_b, att_wt, att_w, grad_out, \
+                                                             grad_x, grad_enc_w, grad_enc_b, grad_att_w, ws, n, st);
   B200_LFA_BWD_CASES(X)
 #undef X
   set_error("b200_lfa_bwd: unsupported (c=%d, kt=%d); c in {8,16,32,64,128,256}, kt in {16,32}", c, kt);

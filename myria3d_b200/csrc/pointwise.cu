@@ -54,6 +54,16 @@ __device__ __forceinline__ float4 dense_load4(const float* __restrict__ p, int64
   return v;
 }
 
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+static CatRows make_cat(const float* a1, int64_t ld1, int c1, const float* a2, int64_t ld2, int c2) {
+  CatRows A{a1, ld1, c1, a2, ld2, c2, false};
+  bool v = aligned16(a1) && (ld1 % 4 == 0) && (c1 % 4 == 0);
+  if (c2 > 0) v = v && aligned16(a2) && (ld2 % 4 == 0) && (c2 % 4 == 0);
+  A.vec = v;
+  return A;
+}
+
 template <int BM, int BN>
 struct GemmTile {
   static constexpr int TM = BM / 16, TN = BN / 16;
@@ -86,7 +96,7 @@ struct GemmTile {
 template <int BM, int BN>
 __global__ void __launch_bounds__(GEMM_THREADS)
 linear_fwd_kernel(CatRows A, const float* __restrict__ w, bool wvec, const float* __restrict__ bias,
-                  float* __restrict__ y, int64_t n, int cout, double* __restrict__ colstats) {
+                  float* __restrict__ y, int64_t n, int cout, double* __restrict__ colstats /* [row tiles][2*cout] */) {
   __shared__ __align__(16) float As[GEMM_BK][BM + 4];
   __shared__ __align__(16) float Bs[GEMM_BK][BN + 4];
   __shared__ double cs[2][BN];
@@ -147,11 +157,13 @@ linear_fwd_kernel(CatRows A, const float* __restrict__ w, bool wvec, const float
       atomicAdd(&cs[1][tx * TN + s], psq[s]);
     }
     __syncthreads();
+    // one partial row per row tile, written (not accumulated): no global atomics, no zero-fill needed
+    double* part = colstats + (int64_t)blockIdx.x * 2 * cout;
     for (int t = tid; t < BN; t += GEMM_THREADS) {
       const int col = col0 + t;
       if (col < cout) {
-        atomicAdd(colstats + col, cs[0][t]);
-        atomicAdd(colstats + cout + col, cs[1][t]);
+        part[col] = cs[0][t];
+        part[cout + col] = cs[1][t];
       }
     }
   }
@@ -270,18 +282,210 @@ linear_bwd_weight_kernel(const float* __restrict__ gy, bool gvec, CatRows A, flo
   }
 }
 
+// ------------------------------------------------------------------ tall-skinny gw += gy^T [a1|a2|1]
+// Level-0/1 layers: hundreds of thousands of rows, <= 64 channels on both sides.  A tile GEMM spends its time
+// on barriers there; instead each WARP streams 16-row chunks through its private shared-memory slab and every
+// lane keeps the outer-product column(s) it owns in registers:
+//   lane l owns activation columns l and l+32; acc[c] += gy[row][c] * a[row][l]  (gy row: LDS.128 broadcast).
+// The next chunk is fetched into registers (float4, all loads in flight at once) while the current one is
+// being multiplied; one shared-memory reduction and one set of global atomics per CTA at the end.
+constexpr int SK_THREADS = 128;
+constexpr int SK_ROWS = 16;
+
+// AW = activation columns covered (32: lane l owns column l; 64: columns l and l+32).
+// FAST: cout == CO, gy 16-byte aligned, activation segments float4-addressable (CatRows::vec).
+template <int CO, int AW, bool FAST>
+__global__ void __launch_bounds__(SK_THREADS)
+tn_skinny_kernel(const float* __restrict__ gy, int cout, CatRows A, float* __restrict__ gw, float* __restrict__ gb,
+                 int64_t n, int64_t rows_per_cta) {
+  constexpr bool TWO = (AW == 64);
+  extern __shared__ __align__(16) float sk_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int NW = SK_THREADS / 32;
+  float* GY = sk_smem + warp * (SK_ROWS * CO + SK_ROWS * AW);  // [SK_ROWS][CO]
+  float* AA = GY + SK_ROWS * CO;                                 // [SK_ROWS][AW]
+  float* R = sk_smem + NW * (SK_ROWS * CO + SK_ROWS * AW);       // [CO][AW] + [CO] CTA reduction buffer
+  const int ktot = A.c1 + A.c2;
+
+  float acc0[CO], acc1[TWO ? CO : 1];
+  float bs0 = 0.f, bs1 = 0.f;  // bias gradient: column sums of gy (lane l: channels l, l + 32)
+#pragma unroll
+  for (int c = 0; c < CO; ++c) acc0[c] = 0.f;
+#pragma unroll
+  for (int c = 0; c < (TWO ? CO : 1); ++c) acc1[c] = 0.f;
+  for (int t = lane; t < SK_ROWS * CO; t += 32) GY[t] = 0.f;  // padded channels stay zero
+  for (int t = lane; t < SK_ROWS * AW; t += 32) AA[t] = 0.f;  // padded columns stay zero
+  for (int t = threadIdx.x; t < CO * AW + CO; t += SK_THREADS) R[t] = 0.f;
+  __syncwarp();
+
+  const int64_t cta_begin = (int64_t)blockIdx.x * rows_per_cta;
+  const int64_t cta_end = (cta_begin + rows_per_cta < n) ? (cta_begin + rows_per_cta) : n;
+
+  constexpr int GV = SK_ROWS * CO / 4 / 32;  // float4 per lane of a gy chunk (FAST)
+  constexpr int AV = SK_ROWS * AW / 4 / 32;  // float4 per lane of an activation chunk (FAST)
+  constexpr int RV = AW / 4;                 // float4 per activation row
+  float4 gbuf[FAST ? GV : 1], abuf[FAST ? AV : 1];
+  (void)gbuf;
+  (void)abuf;
+
+  auto fetch = [&](int64_t r0) {  // FAST: issue every load of the chunk, keep the data in registers
+    if constexpr (FAST) {
+      const int rows = (int)((cta_end - r0 < SK_ROWS) ? (cta_end - r0) : SK_ROWS);
+      const float4* g4 = reinterpret_cast<const float4*>(gy + r0 * CO);
+#pragma unroll
+      for (int j = 0; j < GV; ++j) {
+        const int t = lane + 32 * j;
+        gbuf[j] = (t / (CO / 4) < rows) ? __ldg(g4 + t) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int j = 0; j < AV; ++j) {
+        const int t = lane + 32 * j;
+        const int row = t / RV, col = (t % RV) * 4;
+        abuf[j] = (row < rows && col < ktot) ? cat_load4(A, r0 + row, col) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+  };
+  auto commit = [&](int64_t r0) {  // registers -> the warp's shared-memory slab (generic path: global -> smem)
+    if constexpr (FAST) {
+#pragma unroll
+      for (int j = 0; j < GV; ++j) reinterpret_cast<float4*>(GY)[lane + 32 * j] = gbuf[j];
+#pragma unroll
+      for (int j = 0; j < AV; ++j) reinterpret_cast<float4*>(AA)[lane + 32 * j] = abuf[j];
+    } else {
+      const int rows = (int)((cta_end - r0 < SK_ROWS) ? (cta_end - r0) : SK_ROWS);
+#pragma unroll 4
+      for (int t = lane; t < SK_ROWS * cout; t += 32) {
+        const int row = t / cout, c = t - row * cout;
+        GY[row * CO + c] = (row < rows) ? __ldg(gy + r0 * cout + t) : 0.f;
+      }
+#pragma unroll 4
+      for (int t = lane; t < SK_ROWS * AW; t += 32) {
+        const int row = t / AW, col = t % AW;
+        if (col < ktot) AA[t] = (row < rows) ? cat_load1(A, r0 + row, col) : 0.f;
+      }
+    }
+  };
+
+  int64_t r0 = cta_begin + warp * SK_ROWS;
+  if (r0 < cta_end) fetch(r0);
+  for (; r0 < cta_end; r0 += NW * SK_ROWS) {
+    commit(r0);
+    __syncwarp();
+    const int64_t rn = r0 + NW * SK_ROWS;
+    if (rn < cta_end) fetch(rn);  // overlaps with the multiply below
+#pragma unroll 4
+    for (int row = 0; row < SK_ROWS; ++row) {
+      const float a0 = AA[row * AW + lane];
+      const float a1 = TWO ? AA[row * AW + 32 + lane] : 0.f;
+      if (lane < CO) bs0 += GY[row * CO + lane];
+      if (CO > 32) bs1 += GY[row * CO + 32 + lane];
+#pragma unroll
+      for (int c4 = 0; c4 < CO / 4; ++c4) {
+        const float4 g = *reinterpret_cast<const float4*>(GY + row * CO + c4 * 4);
+        acc0[c4 * 4 + 0] = fmaf(g.x, a0, acc0[c4 * 4 + 0]);
+        acc0[c4 * 4 + 1] = fmaf(g.y, a0, acc0[c4 * 4 + 1]);
+        acc0[c4 * 4 + 2] = fmaf(g.z, a0, acc0[c4 * 4 + 2]);
+        acc0[c4 * 4 + 3] = fmaf(g.w, a0, acc0[c4 * 4 + 3]);
+        if (TWO) {
+          acc1[c4 * 4 + 0] = fmaf(g.x, a1, acc1[c4 * 4 + 0]);
+          acc1[c4 * 4 + 1] = fmaf(g.y, a1, acc1[c4 * 4 + 1]);
+          acc1[c4 * 4 + 2] = fmaf(g.z, a1, acc1[c4 * 4 + 2]);
+          acc1[c4 * 4 + 3] = fmaf(g.w, a1, acc1[c4 * 4 + 3]);
+        }
+      }
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+#pragma unroll
+  for (int c = 0; c < CO; ++c) {
+    atomicAdd(&R[c * AW + lane], acc0[c]);
+    if (TWO) atomicAdd(&R[c * AW + 32 + lane], acc1[c]);
+  }
+  if (lane < CO) atomicAdd(&R[CO * AW + lane], bs0);
+  if (CO > 32) atomicAdd(&R[CO * AW + 32 + lane], bs1);
+  __syncthreads();
+  for (int t = threadIdx.x; t < CO * AW; t += SK_THREADS) {
+    const int c = t / AW, col = t % AW;
+    if (c < cout && col < ktot) atomicAdd(gw + (int64_t)c * ktot + col, R[t]);
+  }
+  if (gb)
+    for (int c = threadIdx.x; c < cout; c += SK_THREADS) atomicAdd(gb + c, R[CO * AW + c]);
+}
+
+template <int CO, int AW>
+static int launch_tn_skinny(const float* gy, int cout, const CatRows& A, float* gw, float* gb, int64_t n, cudaStream_t st) {
+  const size_t smem = sizeof(float) * ((SK_THREADS / 32) * (SK_ROWS * CO + SK_ROWS * AW) + CO * AW + CO);
+  const bool fast = (cout == CO) && aligned16(gy) && A.vec;
+  auto kern = fast ? tn_skinny_kernel<CO, AW, true> : tn_skinny_kernel<CO, AW, false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return cuda_fail(e, "tn_skinny smem attribute");
+  int64_t ctas = (int64_t)num_sms() * 4;
+  const int64_t max_ctas = ceil_div(n, (SK_THREADS / 32) * SK_ROWS);
+  if (ctas > max_ctas) ctas = max_ctas;
+  int64_t rows_per_cta = ceil_div(n, ctas);
+  rows_per_cta = ceil_div(rows_per_cta, (SK_THREADS / 32) * SK_ROWS) * (SK_THREADS / 32) * SK_ROWS;
+  ctas = ceil_div(n, rows_per_cta);
+  kern<<<(unsigned)ctas, SK_THREADS, smem, st>>>(gy, cout, A, gw, gb, n, rows_per_cta);
+  B200_CHECK_LAUNCH("tn_skinny_kernel");
+  return B200_OK;
+}
+
+// generic dispatcher of gw[cout, c1+c2] += gy^T [a1|a2], gb += colsum(gy)
+static int launch_tn(const float* gy, int cout, const CatRows& A, float* gw, float* gb, int64_t n, cudaStream_t st) {
+  const int ktot = A.c1 + A.c2;
+  const int ncols = ktot + (gb ? 1 : 0);
+  if (cout <= 64 && ktot <= 64 && n >= 4096) {
+    const bool wide = ktot > 32;
+    if (cout <= 16) return wide ? launch_tn_skinny<16, 64>(gy, cout, A, gw, gb, n, st) : launch_tn_skinny<16, 32>(gy, cout, A, gw, gb, n, st);
+    if (cout <= 32) return wide ? launch_tn_skinny<32, 64>(gy, cout, A, gw, gb, n, st) : launch_tn_skinny<32, 32>(gy, cout, A, gw, gb, n, st);
+    return wide ? launch_tn_skinny<64, 64>(gy, cout, A, gw, gb, n, st) : launch_tn_skinny<64, 32>(gy, cout, A, gw, gb, n, st);
+  }
+  const bool gvec = (reinterpret_cast<uintptr_t>(gy) & 15) == 0 && (cout % 4 == 0);
+  const bool big = cout >= 128 && ncols >= 128;
+  const int bm = big ? 128 : 64;
+  const int64_t tiles = ceil_div(cout, bm) * ceil_div(ncols, bm);
+  int64_t splits = ceil_div((int64_t)num_sms() * 2, tiles);  // few CTAs: every CTA ends with cout*ncols global atomics
+  const int64_t max_splits = ceil_div(n, 128);
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  if (splits > 65535) splits = 65535;
+  int64_t rows_per_split = ceil_div(n, splits);
+  rows_per_split = ceil_div(rows_per_split, GEMM_BK) * GEMM_BK;
+  splits = ceil_div(n, rows_per_split);
+  dim3 grid((unsigned)ceil_div(cout, bm), (unsigned)ceil_div(ncols, bm), (unsigned)splits);
+  if (big)
+    linear_bwd_weight_kernel<128, 128><<<grid, GEMM_THREADS, 0, st>>>(gy, gvec, A, gw, gb, n, cout, rows_per_split);
+  else
+    linear_bwd_weight_kernel<64, 64><<<grid, GEMM_THREADS, 0, st>>>(gy, gvec, A, gw, gb, n, cout, rows_per_split);
+  B200_CHECK_LAUNCH("linear_bwd_weight_kernel");
+  return B200_OK;
+}
+
 // ------------------------------------------------------------------ BatchNorm finalisation
-__global__ void bn_finalize_kernel(const double* __restrict__ colstats, int64_t count, const float* __restrict__ gamma,
+__global__ void bn_finalize_kernel(const double* __restrict__ colstats, int num_partials, int64_t count,
+                                   const float* __restrict__ gamma,
                                    const float* __restrict__ beta, float* __restrict__ running_mean,
                                    float* __restrict__ running_var, int64_t* __restrict__ num_batches_tracked,
                                    float momentum, float eps, float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
                                    float* __restrict__ invstd_out, int c) {
   if (blockIdx.x == 0 && threadIdx.x == 0 && colstats && num_batches_tracked) *num_batches_tracked += 1;
-  for (int ch = blockIdx.x * blockDim.x + threadIdx.x; ch < c; ch += gridDim.x * blockDim.x) {
+  // one warp per channel: lanes stride over the partial rows, then a shuffle reduction
+  const int lane = threadIdx.x & 31;
+  const int warps = (blockDim.x >> 5) * gridDim.x;
+  for (int ch = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); ch < c; ch += warps) {
     double mean, var;
     if (colstats) {
-      mean = colstats[ch] / (double)count;
-      var = colstats[c + ch] / (double)count - mean * mean;
+      double s1 = 0.0, s2 = 0.0;
+      for (int p = lane; p < num_partials; p += 32) {
+        s1 += colstats[(int64_t)p * 2 * c + ch];
+        s2 += colstats[(int64_t)p * 2 * c + c + ch];
+      }
+      s1 = warp_sum(s1);
+      s2 = warp_sum(s2);
+      if (lane != 0) continue;
+      mean = s1 / (double)count;
+      var = s2 / (double)count - mean * mean;
       if (var < 0.0) var = 0.0;
       if (running_mean) {
         const double unbiased = (count > 1) ? var * (double)count / (double)(count - 1) : var;
@@ -289,6 +493,7 @@ __global__ void bn_finalize_kernel(const double* __restrict__ colstats, int64_t 
         running_var[ch] = (float)((1.0 - (double)momentum) * (double)running_var[ch] + (double)momentum * unbiased);
       }
     } else {
+      if (lane != 0) continue;
       mean = (double)running_mean[ch];
       var = (double)running_var[ch];
     }
@@ -472,21 +677,16 @@ affine_act_bwd_apply_kernel(const float* __restrict__ go, const float* __restric
   }
 }
 
-static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
-
-static CatRows make_cat(const float* a1, int64_t ld1, int c1, const float* a2, int64_t ld2, int c2) {
-  CatRows A{a1, ld1, c1, a2, ld2, c2, false};
-  bool v = aligned16(a1) && (ld1 % 4 == 0) && (c1 % 4 == 0);
-  if (c2 > 0) v = v && aligned16(a2) && (ld2 % 4 == 0) && (c2 % 4 == 0);
-  A.vec = v;
-  return A;
-}
-
 static int elementwise_grid(int64_t work_items) {
   int64_t blocks = ceil_div(work_items, 256);
   const int64_t cap = (int64_t)num_sms() * 8;
   if (blocks > cap) blocks = cap;
   return (int)(blocks < 1 ? 1 : blocks);
+}
+
+int accumulate_at_b(const float* a, int ca, const float* b, int cb, float* out, int64_t n, cudaStream_t st) {
+  const CatRows B = make_cat(b, cb, cb, nullptr, 0, 0);
+  return launch_tn(a, ca, B, out, nullptr, n, st);
 }
 
 }  // namespace b200
@@ -506,6 +706,9 @@ extern "C" int b200_linear_fwd(const float* a1, int64_t ld1, int32_t c1, const f
   if (cout <= 32) {
     dim3 grid((unsigned)ceil_div(n, 128), (unsigned)ceil_div(cout, 32));
     linear_fwd_kernel<128, 32><<<grid, GEMM_THREADS, 0, st>>>(A, w, wvec, bias, y, n, cout, colstats);
+  } else if (cout >= 128 && c1 + c2 >= 64 && ceil_div(n, 128) * ceil_div(cout, 128) >= num_sms()) {
+    dim3 grid((unsigned)ceil_div(n, 128), (unsigned)ceil_div(cout, 128));
+    linear_fwd_kernel<128, 128><<<grid, GEMM_THREADS, 0, st>>>(A, w, wvec, bias, y, n, cout, colstats);
   } else {
     dim3 grid((unsigned)ceil_div(n, 64), (unsigned)ceil_div(cout, 64));
     linear_fwd_kernel<64, 64><<<grid, GEMM_THREADS, 0, st>>>(A, w, wvec, bias, y, n, cout, colstats);
@@ -526,6 +729,9 @@ extern "C" int b200_linear_bwd_input(const float* grad_y, const float* w, float*
   if (ktot <= 32) {
     dim3 grid((unsigned)ceil_div(n, 128), (unsigned)ceil_div(ktot, 32));
     linear_bwd_input_kernel<128, 32><<<grid, GEMM_THREADS, 0, st>>>(grad_y, gvec, w, wvec, ga1, ldg1, c1, ga2, ldg2, c2, n, cout);
+  } else if (ktot >= 128 && cout >= 64 && ceil_div(n, 128) * ceil_div(ktot, 128) >= num_sms()) {
+    dim3 grid((unsigned)ceil_div(n, 128), (unsigned)ceil_div(ktot, 128));
+    linear_bwd_input_kernel<128, 128><<<grid, GEMM_THREADS, 0, st>>>(grad_y, gvec, w, wvec, ga1, ldg1, c1, ga2, ldg2, c2, n, cout);
   } else {
     dim3 grid((unsigned)ceil_div(n, 64), (unsigned)ceil_div(ktot, 64));
     linear_bwd_input_kernel<64, 64><<<grid, GEMM_THREADS, 0, st>>>(grad_y, gvec, w, wvec, ga1, ldg1, c1, ga2, ldg2, c2, n, cout);
@@ -542,24 +748,18 @@ extern "C" int b200_linear_bwd_weight(const float* grad_y, const float* a1, int6
   if (n <= 0) return B200_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const CatRows A = make_cat(a1, ld1, c1, a2, ld2, c2);
-  const bool gvec = aligned16(grad_y) && (cout % 4 == 0);
-  const int ncols = c1 + c2 + (grad_bias ? 1 : 0);
-  const int64_t tiles = ceil_div(cout, 64) * ceil_div(ncols, 64);
-  int64_t splits = ceil_div((int64_t)num_sms() * 4, tiles);
-  const int64_t max_splits = ceil_div(n, 128);
-  if (splits > max_splits) splits = max_splits;
-  if (splits < 1) splits = 1;
-  if (splits > 65535) splits = 65535;
-  int64_t rows_per_split = ceil_div(n, splits);
-  rows_per_split = ceil_div(rows_per_split, GEMM_BK) * GEMM_BK;
-  splits = ceil_div(n, rows_per_split);
-  dim3 grid((unsigned)ceil_div(cout, 64), (unsigned)ceil_div(ncols, 64), (unsigned)splits);
-  linear_bwd_weight_kernel<64, 64><<<grid, GEMM_THREADS, 0, st>>>(grad_y, gvec, A, grad_w, grad_bias, n, cout, rows_per_split);
-  B200_CHECK_LAUNCH("linear_bwd_weight_kernel");
-  return B200_OK;
+  return launch_tn(grad_y, cout, A, grad_w, grad_bias, n, st);
 }
 
-extern "C" int b200_bn_finalize(const double* colstats, int64_t count, const float* gamma, const float* beta,
+extern "C" int64_t b200_linear_fwd_num_stat_partials(int64_t n, int32_t c1, int32_t c2, int32_t cout) {
+  if (n <= 0) return 0;
+  if (cout <= 32) return ceil_div(n, 128);
+  if (cout >= 128 && c1 + c2 >= 64 && ceil_div(n, 128) * ceil_div(cout, 128) >= num_sms()) return ceil_div(n, 128);
+  return ceil_div(n, 64);
+}
+
+extern "C" int b200_bn_finalize(const double* colstats, int32_t num_partials, int64_t count, const float* gamma,
+                                const float* beta,
                                 float* running_mean, float* running_var, int64_t* num_batches_tracked, float momentum,
                                 float eps, float* scale, float* shift, float* mean, float* invstd, int32_t c,
                                 void* stream) {
@@ -569,8 +769,9 @@ extern "C" int b200_bn_finalize(const double* colstats, int64_t count, const flo
   B200_REQUIRE(!colstats || count > 0, B200_E_INVALID, "b200_bn_finalize: count must be positive");
   B200_REQUIRE((running_mean == nullptr) == (running_var == nullptr), B200_E_INVALID,
                "b200_bn_finalize: running_mean / running_var must come together");
-  bn_finalize_kernel<<<(unsigned)ceil_div(c, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
-      colstats, count, gamma, beta, running_mean, running_var, num_batches_tracked, momentum, eps, scale, shift, mean,
+  B200_REQUIRE(!colstats || num_partials >= 1, B200_E_INVALID, "b200_bn_finalize: num_partials must be >= 1");
+  bn_finalize_kernel<<<(unsigned)ceil_div(c, 4), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      colstats, num_partials, count, gamma, beta, running_mean, running_var, num_batches_tracked, momentum, eps, scale, shift, mean,
       invstd, c);
   B200_CHECK_LAUNCH("bn_finalize_kernel");
   return B200_OK;

@@ -191,8 +191,10 @@ class _LFAFunction(torch.autograd.Function):
         gew = torch.zeros_like(enc_w)
         geb = torch.zeros_like(enc_b)
         gaw = torch.zeros_like(att_w)
-        _call("b200_lfa_bwd", _p(x), _p(pos), _p(nbr), _p(enc_w), _p(enc_b), _p(att_wt), _p(att_w),
-                                      _p(grad_out), _p(gx), _p(gew), _p(geb), _p(gaw), n, c, nbr.shape[1], _stream())
+        nbytes = int(_lib.load().b200_lfa_bwd_workspace_bytes(n, c, nbr.shape[1]))
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device) if nbytes else None
+        _call("b200_lfa_bwd", _p(x), _p(pos), _p(nbr), _p(enc_w), _p(enc_b), _p(att_wt), _p(att_w), _p(grad_out),
+              _p(gx), _p(gew), _p(geb), _p(gaw), _p(ws), nbytes, n, c, nbr.shape[1], _stream())
         return gx, None, None, gew, geb, gaw
 
 
@@ -285,7 +287,10 @@ class _Linear(torch.autograd.Function):
         if w.shape[1] != c1 + c2:
             raise RuntimeError(f"mat1 and mat2 shapes cannot be multiplied ({n}x{c1 + c2} and {w.shape[1]}x{cout})")
         y = torch.empty((n, cout), dtype=torch.float32, device=a1.device)
-        stats = torch.zeros(2 * cout, dtype=torch.float64, device=a1.device) if want_stats else None
+        stats = None
+        if want_stats:  # per-row-tile partial sums [P, 2*cout]; written by the kernel, summed by bn_finalize
+            parts = int(_lib.load().b200_linear_fwd_num_stat_partials(n, c1, c2, cout))
+            stats = torch.empty((max(parts, 1), 2 * cout), dtype=torch.float64, device=a1.device)
         _call("b200_linear_fwd", _p(a1), c1, c1, _p(a2), c2, c2, _p(w), _p(b), _p(y), n, cout, _p(stats), _stream())
         ctx.save_for_backward(a1, a2, w)
         ctx.has_bias = b is not None
@@ -338,7 +343,8 @@ class _BNAct(torch.autograd.Function):
 
         def finalize(stats, g, b, rm, rv, nbt):
             buf = torch.empty((4, c), dtype=torch.float32, device=dev)  # scale, shift, mean, invstd
-            _call("b200_bn_finalize", _p(stats), n, _p(g), _p(b), _p(rm), _p(rv), _p(nbt), momentum, eps,
+            parts = stats.shape[0] if stats is not None else 0
+            _call("b200_bn_finalize", _p(stats), parts, n, _p(g), _p(b), _p(rm), _p(rv), _p(nbt), momentum, eps,
                                       _p(buf[0]), _p(buf[1]), _p(buf[2]), _p(buf[3]), c, _stream())
             return buf
 

@@ -232,6 +232,7 @@ def test_linear_stats_cancellation(lib):
         b = torch.randn(8, generator=g) + 50.0
         yr = F.linear(a, w, b).double()
         y, stats = ops.linear(a.to(DEV), w.to(DEV), b.to(DEV), want_stats=True)
+        stats = stats.sum(0)
         mean = stats[:8] / n
         var = stats[8:] / n - mean * mean
         assert_close(y, yr, atol=2e-5, what="y")
@@ -260,6 +261,7 @@ def test_linear_fwd_bwd(lib, n, c1, c2, cout):
     y.backward(gy.to(DEV))
     tol = 1e-5 * (c1 + c2) ** 0.5
     assert_close(y, yr, atol=tol, rtol=1e-5, what="linear y")
+    stats = stats.sum(0)  # per-row-tile partials
     assert_close(stats[:cout], yr.double().sum(0), atol=1e-3, rtol=1e-5, what="column sums")
     assert_close(stats[cout:], (yr.double() ** 2).sum(0), atol=1e-3, rtol=1e-5, what="column sums of squares")
     assert_close(ag[0].grad, ar[0].grad, atol=1e-5 * cout ** 0.5 * 3, rtol=1e-5, what="grad a1")
@@ -303,7 +305,7 @@ def test_bn_act(lib, n, c, dual, training):
 
     def stats(t):
         td = t.detach().double()
-        return torch.cat([td.sum(0), (td * td).sum(0)]) if training else None
+        return torch.cat([td.sum(0), (td * td).sum(0)])[None, :].contiguous() if training else None
 
     out = ops.bn_act(d1, stats(d1), gb1, 0.2, y2=d2 if dual else None, stats2=stats(d2) if dual else None,
                      bn2=gb2 if dual else None)
@@ -327,7 +329,7 @@ def test_bn_single_row_raises(lib):
     bn = torch.nn.BatchNorm1d(8).to(DEV)
     y = torch.randn(1, 8, device=DEV)
     with pytest.raises(ValueError):
-        ops.bn_act(y, torch.zeros(16, dtype=torch.float64, device=DEV), bn, 0.2)
+        ops.bn_act(y, torch.zeros((1, 16), dtype=torch.float64, device=DEV), bn, 0.2)
 
 
 # ------------------------------------------------------------------------------- index / scatter
