@@ -221,6 +221,14 @@ int b200_affine_act_bwd_apply(const float* grad_out, const float* out, float slo
                               float* grad_gamma2, float* grad_beta2,
                               int64_t n, int32_t c, void* stream);
 
+/* ------------------------------------------------------- tcgen05 self-test --------------
+ * d[128, n] = a[128, k] * b[n, k]^T on the 5th-generation tensor cores (tcgen05.mma kind::tf32, TMEM
+ * accumulator), with 1 (plain TF32) or 3 (3xTF32 split, fp32-grade) passes.  Pins the shared-memory
+ * descriptor / TMEM conventions of the fused kernels.  *status (device int32): 0 = ok, 1 = the MMA
+ * completion barrier timed out.  16 <= n <= 256, n % 16 == 0, k % 8 == 0. */
+int b200_tc_gemm_selftest(const float* a, const float* b, float* d, int32_t n, int32_t k, int32_t passes,
+                          int32_t* status, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,111 @@
+// tcgen05 / TMEM building blocks for sm_100a (inline PTX; bit layouts follow the CUTLASS sm100 headers:
+// cute/arch/mma_sm100_desc.hpp `SmemDescriptor` / `InstrDescriptor`, cute/atom/mma_traits_sm100.hpp
+// `make_umma_desc`).
+//
+// Operand layout used throughout: K-major, NO swizzle ("interleave") canonical layout.  In 16-byte units
+// (= 4 fp32 / tf32 values) an [R rows x K] operand is stored as
+//       chunk(r, j) = (r % 8) + (r / 8) * SBO + j * LBO          j = k / 4
+// i.e. 8-row x 16-byte core matrices; we choose SBO = 8 units (128 B: row groups back to back) and
+// LBO = R + 1 units (one k-chunk of ALL rows, padded by 16 B so that lanes reading the same row at different
+// k-chunks hit different banks).  The array is therefore  float smem[K/4][R+1][4].
+#pragma once
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace b200 {
+namespace tc {
+
+__device__ __forceinline__ uint32_t lbo_bytes(int rows) { return (uint32_t)(rows + 1) * 16u; }
+constexpr uint32_t kSboBytes = 128u;
+
+// float offset of element (row r, k) inside an operand tile of `rows` rows
+__device__ __forceinline__ int operand_offset(int rows, int r, int k) { return ((k >> 2) * (rows + 1) + r) * 4 + (k & 3); }
+__host__ __device__ constexpr size_t operand_floats(int rows, int k) { return (size_t)(k / 4) * (rows + 1) * 4; }
+
+// shared-memory matrix descriptor (K-major, no swizzle, descriptor version 1 = Blackwell)
+__device__ __forceinline__ uint64_t smem_desc(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFFu);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+
+// instruction descriptor: D fp32, A/B tf32, both K-major, dense
+__host__ __device__ constexpr uint32_t idesc_tf32(int m, int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_slot, uint32_t ncols) {  // one full warp
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {  // the same warp
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// make generic-proxy shared-memory writes visible to the async proxy (the tensor core reads smem through it)
+__device__ __forceinline__ void fence_smem_to_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem]^T, one elected thread issues
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"((uint32_t)accumulate)
+      : "memory");
+}
+// arrive on an mbarrier when all previously issued MMAs of this thread have completed
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// bounded wait: false on timeout (a wrong descriptor must not hang the GPU box)
+__device__ __forceinline__ bool mbar_wait_bounded(uint64_t* bar, uint32_t parity, uint32_t max_polls = 4000000u) {
+  for (uint32_t i = 0; i < max_polls; ++i) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (ok) return true;
+  }
+  return false;
+}
+
+// 16 consecutive fp32 columns of this thread's TMEM lane (warp w of the CTA owns lanes 32*(w%4) .. +31)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// 3xTF32 split: v ~= hi + lo with both exactly representable in tf32 (error ~2^-21 |v|)
+__device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
+  uint32_t h, l;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
+  hi = __uint_as_float(h);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(v - hi));
+  lo = __uint_as_float(l);
+}
+
+}  // namespace tc
+}  // namespace b200

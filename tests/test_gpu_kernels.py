@@ -372,3 +372,28 @@ def test_knn_interpolate_bit_exact(lib, k, c):
     out.backward(go.to(DEV))
     assert torch.equal(out.cpu(), ref.detach()), f"max diff {(out.cpu() - ref.detach()).abs().max()}"
     assert_close(xg.grad, xr.grad, atol=1e-5, rtol=1e-5, what="interp grad")
+
+
+# ------------------------------------------------------------------------------ tcgen05 building blocks
+@pytest.mark.parametrize("n,k", [(128, 64), (64, 32), (256, 64), (16, 8), (128, 8)])
+def test_tcgen05_gemm_selftest(lib, n, k):
+    """tcgen05.mma kind::tf32 through our shared-memory descriptors + TMEM load path vs an fp64 product:
+    plain TF32 ~1e-3 relative, 3xTF32 ~1e-6 (fp32-grade)."""
+    from ctypes import c_void_p
+
+    g = torch.Generator().manual_seed(n + k)
+    a = torch.randn(128, k, generator=g)
+    b = torch.randn(n, k, generator=g)
+    ref = (a.double() @ b.double().t())
+    scale = float(ref.abs().max())
+    for passes, tol in ((1, 3e-3), (3, 2e-6)):
+        d = torch.full((128, n), float("nan"), device=DEV)
+        status = torch.zeros(1, dtype=torch.int32, device=DEV)
+        rc = lib.b200_tc_gemm_selftest(c_void_p(a.to(DEV).data_ptr()), c_void_p(b.to(DEV).data_ptr()), c_void_p(d.data_ptr()),
+                                       n, k, passes, c_void_p(status.data_ptr()),
+                                       c_void_p(torch.cuda.current_stream().cuda_stream))
+        assert rc == 0, lib.b200_last_error()
+        torch.cuda.synchronize()
+        assert int(status) == 0, "tcgen05 completion barrier timed out"
+        err = float((d.double().cpu() - ref).abs().max())
+        assert err <= tol * scale, f"passes={passes}: max err {err:.3e} vs scale {scale:.3e}"
