@@ -386,10 +386,11 @@ def test_tcgen05_gemm_selftest(lib, n, k):
     b = torch.randn(n, k, generator=g)
     ref = (a.double() @ b.double().t())
     scale = float(ref.abs().max())
+    ad, bd = a.to(DEV), b.to(DEV)  # keep the device copies alive (the caching allocator would recycle temporaries)
     for passes, tol in ((1, 3e-3), (3, 2e-6)):
         d = torch.full((128, n), float("nan"), device=DEV)
         status = torch.zeros(1, dtype=torch.int32, device=DEV)
-        rc = lib.b200_tc_gemm_selftest(c_void_p(a.to(DEV).data_ptr()), c_void_p(b.to(DEV).data_ptr()), c_void_p(d.data_ptr()),
+        rc = lib.b200_tc_gemm_selftest(c_void_p(ad.data_ptr()), c_void_p(bd.data_ptr()), c_void_p(d.data_ptr()),
                                        n, k, passes, c_void_p(status.data_ptr()),
                                        c_void_p(torch.cuda.current_stream().cuda_stream))
         assert rc == 0, lib.b200_last_error()
