@@ -152,7 +152,7 @@ def algorithmic_bytes(name: str, a):
         _l1, c1, _l2, c2, n, cout = a
         return 4 * n * (c1 + c2 + cout)
     if name == "b200_linear_bwd_weight":
-        _l1, c1, _l2, c2, n, cout = a
+        _l1, c1, _l2, c2, _ws, n, cout = a
         return 4 * n * (c1 + c2 + cout)
     if name == "b200_affine_act_fwd":
         n, c = a

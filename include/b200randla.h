@@ -180,10 +180,15 @@ int b200_linear_fwd(const float* a1, int64_t ld1, int32_t c1, const float* a2, i
 int b200_linear_bwd_input(const float* grad_y, const float* w, float* ga1, int64_t ldg1, int32_t c1,
                           float* ga2, int64_t ldg2, int32_t c2, int64_t n, int32_t cout, void* stream);
 /* grad_w[cout, c1+c2] += grad_y^T [a1|a2];  grad_bias[cout] += column sums of grad_y
- * (both accumulated with atomics: caller zero-fills; grad_bias may be NULL). */
+ * (both ACCUMULATED: caller zero-fills; grad_bias may be NULL).  >= 64 x 64 weights run on the tensor cores
+ * (tcgen05, 3xTF32 split: fp32-grade accuracy).  `workspace` (optional; 16-byte aligned,
+ * b200_linear_bwd_weight_workspace_bytes() bytes) lets the split-K partial tiles be reduced by a second
+ * kernel instead of global atomics (faster and deterministic); NULL selects the atomic path. */
+int64_t b200_linear_bwd_weight_workspace_bytes(int64_t n, int32_t c1, int32_t c2, int32_t cout, int32_t has_bias);
 int b200_linear_bwd_weight(const float* grad_y, const float* a1, int64_t ld1, int32_t c1,
                            const float* a2, int64_t ld2, int32_t c2,
-                           float* grad_w, float* grad_bias, int64_t n, int32_t cout, void* stream);
+                           float* grad_w, float* grad_bias, void* workspace, int64_t workspace_bytes,
+                           int64_t n, int32_t cout, void* stream);
 
 /* BatchNorm statistics -> per-channel affine.  colstats fp64 [num_partials, 2*c] = partial (sum, sum of
  * squares) rows that add up to the statistics over `count` rows.  Writes scale = gamma*invstd, shift = beta - mean*scale, and

@@ -35,7 +35,16 @@ int num_sms();
   } while (0)
 
 // out[m][k] += sum_i a[i][m] * b[i][k]  (a: [n, ca], b: [n, cb], out: [ca, cb]; split-K over n, atomics)
-int accumulate_at_b(const float* a, int ca, const float* b, int cb, float* out, int64_t n, cudaStream_t st);
+int accumulate_at_b(const float* a, int ca, const float* b, int cb, float* out, int64_t n, float* ws, size_t ws_bytes,
+                    cudaStream_t st);
+size_t accumulate_at_b_workspace_bytes(int ca, int cb, int64_t n);
+
+// tensor-core (tcgen05, 3xTF32) version of the same contraction, two-segment activation rows + bias column
+// `ws` (optional, tc_tn_workspace_bytes()): per-split partial tiles + a reduction kernel instead of atomics
+int launch_tc_tn(const float* gy, int cout, const float* a1, int64_t ld1, int c1, const float* a2, int64_t ld2, int c2,
+                 float* gw, float* gb, int64_t n, float* ws, size_t ws_bytes, cudaStream_t st);
+size_t tc_tn_workspace_bytes(int cout, int ncols, int64_t n);
+bool tensor_cores_enabled();  // false iff B200_DISABLE_TCGEN05=1 (A/B switch for tests and profiles)
 
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

@@ -646,8 +646,11 @@ static int launch_lfa_bwd(const float* x, const float* pos, const int32_t* nbr, 
   kern<<<grid, Cfg::THREADS, smem, st>>>(x, pos, nbr, enc_w, enc_b, att_wt, att_w, go, gx, gew, geb, gaw, da_out,
                                          f_out, n, ntiles);
   B200_CHECK_LAUNCH("lfa_bwd_kernel");
-  if (SPLIT_DW)  // dW_att[n][m] += sum_e DA[e][n] F[e][m]: split-K GEMM over the streamed edge rows
-    return accumulate_at_b(da_out, Cfg::C, f_out, Cfg::C, gaw, n * Cfg::KT, st);
+  if (SPLIT_DW) {  // dW_att[n][m] += sum_e DA[e][n] F[e][m]: split-K GEMM over the streamed edge rows
+    float* part = ws + 2 * n * Cfg::KT * Cfg::C;
+    return accumulate_at_b(da_out, Cfg::C, f_out, Cfg::C, gaw, n * Cfg::KT, part,
+                           accumulate_at_b_workspace_bytes(Cfg::C, Cfg::C, n * Cfg::KT), st);
+  }
   return B200_OK;
 }
 
@@ -698,7 +701,7 @@ extern "C" int b200_lfa_fwd(const float* x, const float* pos, const int32_t* nbr
 
 extern "C" int64_t b200_lfa_bwd_workspace_bytes(int64_t n, int32_t c, int32_t kt) {
   if (n <= 0 || c < 64) return 0;
-  return 2 * n * (int64_t)kt * c * (int64_t)sizeof(float);
+  return 2 * n * (int64_t)kt * c * (int64_t)sizeof(float) + (int64_t)b200::accumulate_at_b_workspace_bytes(c, c, n * kt);
 }
 
 extern "C" int b200_lfa_bwd(const float* x, const float* pos, const int32_t* nbr, const float* enc_w,

@@ -109,20 +109,47 @@ linear_fwd_kernel(CatRows A, const float* __restrict__ w, bool wvec, const float
   if (colstats)
     for (int t = tid; t < 2 * BN; t += GEMM_THREADS) (&cs[0][0])[t] = 0.0;
 
-  for (int k0 = 0; k0 < ktot; k0 += GEMM_BK) {
-    for (int s = tid; s < BM * 4; s += GEMM_THREADS) {
+  // register-staged double buffering: the global loads of slice k0+16 are in flight while slice k0 is multiplied
+  constexpr int NA = (BM * 4 + GEMM_THREADS - 1) / GEMM_THREADS, NB = (BN * 4 + GEMM_THREADS - 1) / GEMM_THREADS;
+  float4 ra[NA], rb[NB];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int q = 0; q < NA; ++q) {
+      const int s = tid + q * GEMM_THREADS;
       const int r = s >> 2, kq = s & 3;
       const int64_t row = row0 + r;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (row < n) v = cat_load4(A, row, k0 + kq * 4);
-      As[kq * 4 + 0][r] = v.x, As[kq * 4 + 1][r] = v.y, As[kq * 4 + 2][r] = v.z, As[kq * 4 + 3][r] = v.w;
+      ra[q] = (s < BM * 4 && row < n) ? cat_load4(A, row, k0 + kq * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    for (int s = tid; s < BN * 4; s += GEMM_THREADS) {
+#pragma unroll
+    for (int q = 0; q < NB; ++q) {
+      const int s = tid + q * GEMM_THREADS;
       const int r = s >> 2, kq = s & 3;
-      const float4 v = dense_load4(w, cout, ktot, wvec, col0 + r, k0 + kq * 4);
-      Bs[kq * 4 + 0][r] = v.x, Bs[kq * 4 + 1][r] = v.y, Bs[kq * 4 + 2][r] = v.z, Bs[kq * 4 + 3][r] = v.w;
+      rb[q] = (s < BN * 4) ? dense_load4(w, cout, ktot, wvec, col0 + r, k0 + kq * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
+  };
+  auto commit = [&]() {
+#pragma unroll
+    for (int q = 0; q < NA; ++q) {
+      const int s = tid + q * GEMM_THREADS;
+      if (s < BM * 4) {
+        const int r = s >> 2, kq = s & 3;
+        As[kq * 4 + 0][r] = ra[q].x, As[kq * 4 + 1][r] = ra[q].y, As[kq * 4 + 2][r] = ra[q].z, As[kq * 4 + 3][r] = ra[q].w;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < NB; ++q) {
+      const int s = tid + q * GEMM_THREADS;
+      if (s < BN * 4) {
+        const int r = s >> 2, kq = s & 3;
+        Bs[kq * 4 + 0][r] = rb[q].x, Bs[kq * 4 + 1][r] = rb[q].y, Bs[kq * 4 + 2][r] = rb[q].z, Bs[kq * 4 + 3][r] = rb[q].w;
+      }
+    }
+  };
+  fetch(0);
+  for (int k0 = 0; k0 < ktot; k0 += GEMM_BK) {
+    commit();
     __syncthreads();
+    if (k0 + GEMM_BK < ktot) fetch(k0 + GEMM_BK);
     T.mac(As, Bs, ty, tx);
     __syncthreads();
   }
@@ -184,18 +211,43 @@ linear_bwd_input_kernel(const float* __restrict__ gy, bool gvec, const float* __
   GemmTile<BM, BN> T;
   T.zero();
 
-  for (int k0 = 0; k0 < cout; k0 += GEMM_BK) {
-    for (int s = tid; s < BM * 4; s += GEMM_THREADS) {
+  constexpr int NA = (BM * 4 + GEMM_THREADS - 1) / GEMM_THREADS;
+  constexpr int NB = (GEMM_BK * (BN / 4) + GEMM_THREADS - 1) / GEMM_THREADS;
+  float4 ra[NA], rb[NB];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int q = 0; q < NA; ++q) {
+      const int s = tid + q * GEMM_THREADS;
       const int r = s >> 2, kq = s & 3;
-      const float4 v = dense_load4(gy, n, cout, gvec, row0 + r, k0 + kq * 4);
-      As[kq * 4 + 0][r] = v.x, As[kq * 4 + 1][r] = v.y, As[kq * 4 + 2][r] = v.z, As[kq * 4 + 3][r] = v.w;
+      ra[q] = (s < BM * 4) ? dense_load4(gy, n, cout, gvec, row0 + r, k0 + kq * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    for (int s = tid; s < GEMM_BK * (BN / 4); s += GEMM_THREADS) {
+#pragma unroll
+    for (int q = 0; q < NB; ++q) {
+      const int s = tid + q * GEMM_THREADS;
       const int kk = s / (BN / 4), cq = s % (BN / 4);
-      const float4 v = dense_load4(w, cout, ktot, wvec, k0 + kk, col0 + cq * 4);
-      *reinterpret_cast<float4*>(&Bs[kk][cq * 4]) = v;
+      rb[q] = (s < GEMM_BK * (BN / 4)) ? dense_load4(w, cout, ktot, wvec, k0 + kk, col0 + cq * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
+  };
+  auto commit = [&]() {
+#pragma unroll
+    for (int q = 0; q < NA; ++q) {
+      const int s = tid + q * GEMM_THREADS;
+      if (s < BM * 4) {
+        const int r = s >> 2, kq = s & 3;
+        As[kq * 4 + 0][r] = ra[q].x, As[kq * 4 + 1][r] = ra[q].y, As[kq * 4 + 2][r] = ra[q].z, As[kq * 4 + 3][r] = ra[q].w;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < NB; ++q) {
+      const int s = tid + q * GEMM_THREADS;
+      if (s < GEMM_BK * (BN / 4)) *reinterpret_cast<float4*>(&Bs[s / (BN / 4)][(s % (BN / 4)) * 4]) = rb[q];
+    }
+  };
+  fetch(0);
+  for (int k0 = 0; k0 < cout; k0 += GEMM_BK) {
+    commit();
     __syncthreads();
+    if (k0 + GEMM_BK < cout) fetch(k0 + GEMM_BK);
     T.mac(As, Bs, ty, tx);
     __syncthreads();
   }
@@ -432,9 +484,18 @@ static int launch_tn_skinny(const float* gy, int cout, const CatRows& A, float* 
 }
 
 // generic dispatcher of gw[cout, c1+c2] += gy^T [a1|a2], gb += colsum(gy)
-static int launch_tn(const float* gy, int cout, const CatRows& A, float* gw, float* gb, int64_t n, cudaStream_t st) {
+static bool tn_uses_tensor_cores(const float* gy, int cout, const CatRows& A, const float* gw, int64_t n) {
+  return cout >= 64 && A.c1 + A.c2 >= 64 && n >= 1024 && cout % 4 == 0 && A.vec && aligned16(gy) && aligned16(gw) &&
+         tensor_cores_enabled();
+}
+
+static int launch_tn(const float* gy, int cout, const CatRows& A, float* gw, float* gb, int64_t n, float* ws,
+                     size_t ws_bytes, cudaStream_t st) {
   const int ktot = A.c1 + A.c2;
   const int ncols = ktot + (gb ? 1 : 0);
+  // >= 64 x 64 outputs: 5th-generation tensor cores (3xTF32), see tc_gemm.cu
+  if (tn_uses_tensor_cores(gy, cout, A, gw, n))
+    return launch_tc_tn(gy, cout, A.a1, A.ld1, A.c1, A.a2, A.ld2, A.c2, gw, gb, n, ws, ws_bytes, st);
   if (cout <= 64 && ktot <= 64 && n >= 4096) {
     const bool wide = ktot > 32;
     if (cout <= 16) return wide ? launch_tn_skinny<16, 64>(gy, cout, A, gw, gb, n, st) : launch_tn_skinny<16, 32>(gy, cout, A, gw, gb, n, st);
@@ -684,10 +745,12 @@ static int elementwise_grid(int64_t work_items) {
   return (int)(blocks < 1 ? 1 : blocks);
 }
 
-int accumulate_at_b(const float* a, int ca, const float* b, int cb, float* out, int64_t n, cudaStream_t st) {
+int accumulate_at_b(const float* a, int ca, const float* b, int cb, float* out, int64_t n, float* ws, size_t ws_bytes,
+                    cudaStream_t st) {
   const CatRows B = make_cat(b, cb, cb, nullptr, 0, 0);
-  return launch_tn(a, ca, B, out, nullptr, n, st);
+  return launch_tn(a, ca, B, out, nullptr, n, ws, ws_bytes, st);
 }
+size_t accumulate_at_b_workspace_bytes(int ca, int cb, int64_t n) { return tc_tn_workspace_bytes(ca, cb, n); }
 
 }  // namespace b200
 
@@ -740,15 +803,27 @@ extern "C" int b200_linear_bwd_input(const float* grad_y, const float* w, float*
   return B200_OK;
 }
 
+namespace b200 { void set_tc_debug_buffer(long long* p); }
+// Debug hook (not part of the ABI header): device buffer of 128 int64 receiving clock64() marks of CTA 0.
+extern "C" void b200_debug_set_tc_timeline(long long* p) { b200::set_tc_debug_buffer(p); }
+
+extern "C" int64_t b200_linear_bwd_weight_workspace_bytes(int64_t n, int32_t c1, int32_t c2, int32_t cout, int32_t has_bias) {
+  if (n <= 0 || cout < 64 || c1 + c2 < 64) return 0;
+  return (int64_t)tc_tn_workspace_bytes(cout, c1 + c2 + (has_bias ? 1 : 0), n);
+}
+
 extern "C" int b200_linear_bwd_weight(const float* grad_y, const float* a1, int64_t ld1, int32_t c1, const float* a2,
-                                      int64_t ld2, int32_t c2, float* grad_w, float* grad_bias, int64_t n,
-                                      int32_t cout, void* stream) {
+                                      int64_t ld2, int32_t c2, float* grad_w, float* grad_bias, void* workspace,
+                                      int64_t workspace_bytes, int64_t n, int32_t cout, void* stream) {
   B200_REQUIRE(grad_y && a1 && grad_w, B200_E_INVALID, "b200_linear_bwd_weight: null pointer");
   B200_REQUIRE(c1 > 0 && c2 >= 0 && cout > 0 && (c2 == 0 || a2), B200_E_INVALID, "b200_linear_bwd_weight: bad sizes");
   if (n <= 0) return B200_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const CatRows A = make_cat(a1, ld1, c1, a2, ld2, c2);
-  return launch_tn(grad_y, cout, A, grad_w, grad_bias, n, st);
+  B200_REQUIRE(!workspace || (reinterpret_cast<uintptr_t>(workspace) & 15) == 0, B200_E_INVALID,
+               "b200_linear_bwd_weight: workspace must be 16-byte aligned");
+  return launch_tn(grad_y, cout, A, grad_w, grad_bias, n, static_cast<float*>(workspace),
+                   workspace ? (size_t)workspace_bytes : 0, st);
 }
 
 extern "C" int64_t b200_linear_fwd_num_stat_partials(int64_t n, int32_t c1, int32_t c2, int32_t cout) {

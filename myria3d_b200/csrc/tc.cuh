@@ -98,13 +98,13 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// 3xTF32 split: v ~= hi + lo with both exactly representable in tf32 (error ~2^-21 |v|)
+// 3xTF32 split: v ~= hi + lo, hi exactly representable in tf32 (round-to-nearest on the 13 dropped mantissa
+// bits, done with integer ops: `cvt.rna.tf32.f32` compiles to a branchy NaN/Inf-aware sequence on sm_100a and made
+// the operand conversion 5x more expensive than the MMAs it feeds).  lo = v - hi is exact in fp32; the tensor core
+// ignores its low 13 bits (relative error <= 2^-10 of lo, i.e. ~2^-21 of v).  Inf/NaN inputs are not special-cased.
 __device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
-  uint32_t h, l;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
-  hi = __uint_as_float(h);
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(v - hi));
-  lo = __uint_as_float(l);
+  hi = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u);
+  lo = v - hi;
 }
 
 }  // namespace tc

@@ -316,7 +316,10 @@ class _Linear(torch.autograd.Function):
         if ctx.needs_input_grad[2] or (ctx.has_bias and ctx.needs_input_grad[3]):
             gw = torch.zeros_like(w)
             gb = torch.zeros(cout, dtype=torch.float32, device=w.device) if ctx.has_bias else None
-            _call("b200_linear_bwd_weight", _p(grad_y), _p(a1), c1, c1, _p(a2), c2, c2, _p(gw), _p(gb), n, cout, _stream())
+            nbytes = int(lib.b200_linear_bwd_weight_workspace_bytes(n, c1, c2, cout, 1 if ctx.has_bias else 0))
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=w.device) if nbytes else None
+            _call("b200_linear_bwd_weight", _p(grad_y), _p(a1), c1, c1, _p(a2), c2, c2, _p(gw), _p(gb), _p(ws), nbytes,
+                  n, cout, _stream())
         return ga1, ga2, gw, gb, None
 
 

@@ -240,6 +240,29 @@ def test_linear_stats_cancellation(lib):
         assert_close(var, ycpu.var(0, unbiased=False), atol=0.0, rtol=1e-6, what=f"variance n={n}")
 
 
+@pytest.mark.parametrize("n,c1,c2,cout", [(5000, 128, 0, 256), (4100, 256, 128, 128), (20000, 64, 0, 64), (3000, 512, 256, 256),
+                                          (1030, 64, 0, 70), (9000, 96, 0, 512)])
+def test_linear_weight_grad_tensor_cores(lib, n, c1, c2, cout):
+    """Weight / bias gradients through the tcgen05 3xTF32 split-K kernel (tc_gemm.cu) vs fp64: fp32-grade."""
+    from myria3d_b200 import ops
+
+    g = torch.Generator().manual_seed(n)
+    a1 = torch.randn(n, c1, generator=g)
+    a2 = torch.randn(n, c2, generator=g) if c2 else None
+    w = torch.randn(cout, c1 + c2, generator=g) / (c1 + c2) ** 0.5
+    b = torch.randn(cout, generator=g)
+    gy = torch.randn(n, cout, generator=g)
+    inp = torch.cat([a1, a2], 1) if c2 else a1
+    gw_ref = gy.double().t() @ inp.double()
+    gb_ref = gy.double().sum(0)
+    ag = [t.to(DEV).requires_grad_(True) for t in (a1, w, b)]
+    a2g = a2.to(DEV) if c2 else None
+    y = ops.linear(ag[0], ag[1], ag[2], a2=a2g)
+    y.backward(gy.to(DEV))
+    assert rel_err(ag[1].grad, gw_ref) < 5e-6, rel_err(ag[1].grad, gw_ref)  # fp32 accumulation over n rows
+    assert rel_err(ag[2].grad, gb_ref) < 5e-6, rel_err(ag[2].grad, gb_ref)
+
+
 @pytest.mark.parametrize("n,c1,c2,cout", [(1000, 9, 0, 32), (777, 32, 32, 32), (130, 512, 256, 256), (2048, 32, 0, 7),
                                           (65, 64, 0, 64), (3, 4, 0, 8), (515, 128, 32, 32)])
 def test_linear_fwd_bwd(lib, n, c1, c2, cout):
