@@ -52,6 +52,7 @@ def parse_args():
     ap.add_argument("--profile-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager", action="store_true", help="launch every kernel from Python instead of replaying the step graph")
+    ap.add_argument("--torch-adam", action="store_true", help="use torch.optim.Adam(fused=True) instead of FlatAdam")
     ap.add_argument("--decimation-rng", choices=["fused", "reference"], default="fused",
                     help="fused: one batched random draw per level; reference: per-cloud torch.randperm like the reference")
     ap.add_argument("--kernel-report", default=None, help="write the per-kernel table (JSON) here")
@@ -261,6 +262,7 @@ def workload_config(args, world, impl="b200"):
     return {
         "workload": f"RandLA-Net full (4 down/4 up), K={K_NEIGHBORS}, {args.points} pts/tile, batch={args.tiles}/GPU "
                     f"(BASELINE configs[1]{'/[2]' if world > 1 else ''})",
+        "optimizer": "torch.optim.Adam(fused)" if getattr(args, "torch_adam", False) else "FlatAdam (b200_adam_flat)",
         "step": "fwd + CrossEntropyLoss + bwd + flat NCCL grad all-reduce (N>1) + Adam; "
                 + ("reference CPU path: eager PyTorch, bounded sample of "
                    f"{args.cpu_tiles} tiles per step" if impl == "reference" else
@@ -304,7 +306,12 @@ def run_b200(args):
     model.train()
     broadcast_module_state(model)
     reducer = FlatGradAllReducer(model)
-    opt = torch.optim.Adam(model.parameters(), lr=LR, capturable=not args.eager, fused=True)
+    if args.torch_adam:
+        opt = torch.optim.Adam(model.parameters(), lr=LR, capturable=not args.eager, fused=True)
+    else:
+        from myria3d_b200.optim import FlatAdam
+
+        opt = FlatAdam(model, lr=LR, reducer=reducer)  # torch.optim.Adam arithmetic, one kernel over flat buffers
     model.model.decimation_rng = args.decimation_rng
     graphed = None if args.eager else GraphedTrainStep(model, opt, reducer, decimation_rng=args.decimation_rng)
 

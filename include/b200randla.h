@@ -226,6 +226,14 @@ int b200_affine_act_bwd_apply(const float* grad_out, const float* out, float slo
                               float* grad_gamma2, float* grad_beta2,
                               int64_t n, int32_t c, void* stream);
 
+/* ------------------------------------------------------- optimizer ----------------------
+ * One Adam update over FLAT fp32 buffers (parameters, gradients, first and second moments), the arithmetic of
+ * torch.optim.Adam(lr, betas, eps) without weight decay / amsgrad (configs/model/optimizer/Adam.yaml uses the
+ * defaults).  *step (device int64) is incremented first and used for the bias corrections, so the call is
+ * CUDA-graph capturable.  All buffers 16-byte aligned. */
+int b200_adam_flat(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                   float lr, float beta1, float beta2, float eps, int64_t* step, void* stream);
+
 /* ------------------------------------------------------- tcgen05 self-test --------------
  * d[128, n] = a[128, k] * b[n, k]^T on the 5th-generation tensor cores (tcgen05.mma kind::tf32, TMEM
  * accumulator), with 1 (plain TF32) or 3 (3xTF32 split, fp32-grade) passes.  Pins the shared-memory

@@ -43,6 +43,20 @@ def _call(name: str, *args) -> None:
     prof.add(name, args, start, end)
 
 
+def _direct_grad(p: Optional[Tensor]) -> Optional[Tensor]:
+    """``p.grad`` when a backward kernel may accumulate straight into it (it exists, is a dense fp32 buffer such
+    as a view of FlatGradAllReducer's flat buffer, and nothing hooks the parameter), else None.  Saves the
+    zero-fill of a temporary and autograd's AccumulateGrad add per parameter; the result (p.grad += g) is the same."""
+    if p is None or not isinstance(p, torch.nn.Parameter) or not p.requires_grad:
+        return None
+    g = p.grad
+    if g is None or g.dtype != torch.float32 or not g.is_contiguous() or g.shape != p.shape or not g.is_cuda:
+        return None
+    if p._backward_hooks or getattr(p, "_post_accumulate_grad_hooks", None):
+        return None
+    return g
+
+
 def _need_cuda(*ts: Optional[Tensor]) -> None:
     for t in ts:
         if t is not None and not t.is_cuda:
@@ -170,6 +184,7 @@ class _LFAFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, pos, nbr, enc_w, enc_b, att_w):
+        ctx.att_param = att_w
         x, enc_w, enc_b, att_w = _f32c(x), _f32c(enc_w), _f32c(enc_b), _f32c(att_w)
         att_wt = att_w.t().contiguous()
         n, h = x.shape
@@ -190,12 +205,13 @@ class _LFAFunction(torch.autograd.Function):
         gx = torch.zeros_like(x)
         gew = torch.zeros_like(enc_w)
         geb = torch.zeros_like(enc_b)
-        gaw = torch.zeros_like(att_w)
+        direct = _direct_grad(ctx.att_param)
+        gaw = direct if direct is not None else torch.zeros_like(att_w)
         nbytes = int(_lib.load().b200_lfa_bwd_workspace_bytes(n, c, nbr.shape[1]))
         ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device) if nbytes else None
         _call("b200_lfa_bwd", _p(x), _p(pos), _p(nbr), _p(enc_w), _p(enc_b), _p(att_wt), _p(att_w), _p(grad_out),
               _p(gx), _p(gew), _p(geb), _p(gaw), _p(ws), nbytes, n, c, nbr.shape[1], _stream())
-        return gx, None, None, gew, geb, gaw
+        return gx, None, None, gew, geb, (None if direct is not None else gaw)
 
 
 def lfa_attentive_pool(x: Tensor, pos: Tensor, nbr: Tensor, enc_w: Tensor, enc_b: Tensor, att_w: Tensor) -> Tensor:
@@ -279,6 +295,7 @@ class _Linear(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, a1, a2, w, b, want_stats):
+        w_param, b_param = w, b
         a1, w = _f32c(a1), _f32c(w)
         a2 = _f32c(a2) if a2 is not None else None
         n, c1 = a1.shape
@@ -294,6 +311,7 @@ class _Linear(torch.autograd.Function):
         _call("b200_linear_fwd", _p(a1), c1, c1, _p(a2), c2, c2, _p(w), _p(b), _p(y), n, cout, _p(stats), _stream())
         ctx.save_for_backward(a1, a2, w)
         ctx.has_bias = b is not None
+        ctx.w_param, ctx.b_param = w_param, b_param
         if want_stats:
             ctx.mark_non_differentiable(stats)
             return y, stats
@@ -314,12 +332,18 @@ class _Linear(torch.autograd.Function):
             _call("b200_linear_bwd_input", _p(grad_y), _p(w), _p(ga1), c1, c1, _p(ga2), c2, c2, n, cout, _stream())
         gw = gb = None
         if ctx.needs_input_grad[2] or (ctx.has_bias and ctx.needs_input_grad[3]):
-            gw = torch.zeros_like(w)
-            gb = torch.zeros(cout, dtype=torch.float32, device=w.device) if ctx.has_bias else None
+            dw = _direct_grad(ctx.w_param)
+            db = _direct_grad(ctx.b_param) if ctx.has_bias else None
+            direct = dw is not None and (not ctx.has_bias or db is not None)
+            if direct:  # the kernels accumulate: write straight into the parameters' .grad
+                gw_buf, gb_buf = dw, db
+            else:
+                gw_buf = gw = torch.zeros_like(w)
+                gb_buf = gb = torch.zeros(cout, dtype=torch.float32, device=w.device) if ctx.has_bias else None
             nbytes = int(lib.b200_linear_bwd_weight_workspace_bytes(n, c1, c2, cout, 1 if ctx.has_bias else 0))
             ws = torch.empty(nbytes, dtype=torch.uint8, device=w.device) if nbytes else None
-            _call("b200_linear_bwd_weight", _p(grad_y), _p(a1), c1, c1, _p(a2), c2, c2, _p(gw), _p(gb), _p(ws), nbytes,
-                  n, cout, _stream())
+            _call("b200_linear_bwd_weight", _p(grad_y), _p(a1), c1, c1, _p(a2), c2, c2, _p(gw_buf), _p(gb_buf), _p(ws),
+                  nbytes, n, cout, _stream())
         return ga1, ga2, gw, gb, None
 
 

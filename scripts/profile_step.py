@@ -17,7 +17,8 @@ model = Model(neural_net_class_name="B200RandLANet", neural_net_hparams=dict(num
               criterion=torch.nn.CrossEntropyLoss(ignore_index=65), lr=bench.LR).to(dev).train()
 red = FlatGradAllReducer(model)
 graphed = "--graphed" in sys.argv
-opt = torch.optim.Adam(model.parameters(), lr=bench.LR, capturable=graphed)
+from myria3d_b200.optim import FlatAdam
+opt = FlatAdam(model, lr=bench.LR, reducer=red)
 b = bench.host_batch(16, 12800, 12345).to(dev)
 step_g = GraphedTrainStep(model, opt, red) if graphed else None
 def step():

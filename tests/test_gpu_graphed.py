@@ -69,3 +69,25 @@ def test_graphed_step_trains(lib):
     step(b2.to(DEV))
     assert len(step._captured) == 2
     assert torch.isfinite(step.last_outputs(b2)["logits"]).all()
+
+
+def test_flat_adam_matches_torch_adam(lib):
+    """b200_adam_flat == torch.optim.Adam on the same gradients over several steps (parameters as flat views)."""
+    from myria3d_b200.optim import FlatAdam
+
+    torch.manual_seed(0)
+    # (no BatchNorm right after a Linear: that Linear's bias has a mathematically zero gradient, whose fp32 noise Adam
+    # normalises to +-lr steps -- any two Adam implementations diverge there by O(lr))
+    net_a = torch.nn.Sequential(torch.nn.Linear(9, 33), torch.nn.Tanh(), torch.nn.Linear(33, 7)).to(DEV)
+    net_b = copy.deepcopy(net_a)
+    opt_a = torch.optim.Adam(net_a.parameters(), lr=3e-3, betas=(0.9, 0.999), eps=1e-8)
+    opt_b = FlatAdam(net_b, lr=3e-3)
+    for s in range(5):
+        x = torch.randn(64, 9, device=DEV)
+        for net, opt in ((net_a, opt_a), (net_b, opt_b)):
+            opt.zero_grad()
+            net(x).square().mean().backward()
+            opt.step()
+    for pa, pb in zip(net_a.parameters(), net_b.parameters()):
+        assert torch.allclose(pa, pb, atol=1e-6, rtol=1e-5), float((pa - pb).abs().max())
+    assert int(opt_b.step_count) == 5
