@@ -96,9 +96,10 @@ edge_moments_kernel(const float* __restrict__ pos, const int32_t* __restrict__ n
 // ------------------------------------------------------------------------------------------
 // tile configuration
 // ------------------------------------------------------------------------------------------
-template <int C_, int KT_, int CW_, int TC_>
+template <int C_, int KT_, int CW_, int TC_, int MINB_ = 3>
 struct LfaCfg {
   static constexpr int C = C_, KT = KT_, CW = CW_, TC = TC_;
+  static constexpr int MINB = MINB_;  // CTAs per SM the register allocator must leave room for
   static constexpr int H = C / 2;
   static constexpr int TPC = C / CW;          // threads per centre
   static constexpr int THREADS = TC * TPC;
@@ -262,22 +263,32 @@ template <class Cfg>
 __device__ __forceinline__ void centre_gemm(float (&acc)[Cfg::KT][Cfg::CW], const float* __restrict__ A,
                                             const float* __restrict__ B, int col0) {
   constexpr int C = Cfg::C, KT = Cfg::KT, CW = Cfg::CW;
+  // register double buffer for the B rows: the loads of rows r0+4..r0+7 are in flight while rows r0..r0+3 are
+  // multiplied (the FFMAs were stalling on these L1/L2 loads: long-scoreboard in the ncu source view)
+  float b[2][4][CW];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) ldg_vec<CW>(b[0][u], B + (int64_t)u * C + col0);
 #pragma unroll 1
-  for (int r0 = 0; r0 < C; r0 += 4) {
-    float b[4][CW];
+  for (int r0 = 0; r0 < C; r0 += 8) {
 #pragma unroll
-    for (int u = 0; u < 4; ++u) ldg_vec<CW>(b[u], B + (int64_t)(r0 + u) * C + col0);
+    for (int half = 0; half < 2; ++half) {
+      const int r = r0 + 4 * half;
+      if (r + 4 < C) {
 #pragma unroll
-    for (int k = 0; k < KT; ++k) {
-      const float4 a = *reinterpret_cast<const float4*>(A + k * C + r0);
+        for (int u = 0; u < 4; ++u) ldg_vec<CW>(b[half ^ 1][u], B + (int64_t)(r + 4 + u) * C + col0);
+      }
 #pragma unroll
-      for (int cw = 0; cw < CW; ++cw) {
-        float v = acc[k][cw];
-        v = fmaf(a.x, b[0][cw], v);
-        v = fmaf(a.y, b[1][cw], v);
-        v = fmaf(a.z, b[2][cw], v);
-        v = fmaf(a.w, b[3][cw], v);
-        acc[k][cw] = v;
+      for (int k = 0; k < KT; ++k) {
+        const float4 a = *reinterpret_cast<const float4*>(A + k * C + r);
+#pragma unroll
+        for (int cw = 0; cw < CW; ++cw) {
+          float v = acc[k][cw];
+          v = fmaf(a.x, b[half][0][cw], v);
+          v = fmaf(a.y, b[half][1][cw], v);
+          v = fmaf(a.z, b[half][2][cw], v);
+          v = fmaf(a.w, b[half][3][cw], v);
+          acc[k][cw] = v;
+        }
       }
     }
   }
@@ -287,7 +298,7 @@ __device__ __forceinline__ void centre_gemm(float (&acc)[Cfg::KT][Cfg::CW], cons
 // forward
 // ------------------------------------------------------------------------------------------
 template <class Cfg>
-__global__ void __launch_bounds__(Cfg::THREADS, (Cfg::THREADS <= 128 ? 3 : 1))
+__global__ void __launch_bounds__(Cfg::THREADS, (Cfg::THREADS <= 128 ? Cfg::MINB : 1))
 lfa_fwd_kernel(const float* __restrict__ x, const float* __restrict__ pos, const int32_t* __restrict__ nbr,
                const float* __restrict__ enc_w, const float* __restrict__ enc_b,
                const float* __restrict__ att_wt, float* __restrict__ out, int64_t n, int64_t ntiles) {
@@ -366,10 +377,14 @@ struct LfaBwdPlan {
   static constexpr int SLICES = (NBLOCKS >= THREADS) ? 1 : (THREADS / NBLOCKS);  // edge slices per block
   static constexpr int PASSES = (NBLOCKS >= THREADS) ? (NBLOCKS / THREADS) : 1;
   static constexpr bool GE_IN_REGS = (C <= 32);      // encoder-gradient partials live in registers
+  // C <= 32: dW[n][m] partials are owned by the thread that already holds da[k][n] in registers (n = its CW columns):
+  // dW[n][:] += da[k][n] * F[k][:] needs only broadcast LDS.128 of the centre's F rows (16 FMA per load) instead of
+  // the 4x4-block GEMM3 whose strided row reads were 4-way bank conflicted and shared-memory bound.
+  static constexpr bool DW_BY_CENTRE = (C <= 32);
 };
 
 template <class Cfg, bool SPLIT_DW>
-__global__ void __launch_bounds__(Cfg::THREADS, (Cfg::THREADS <= 128 ? 3 : 1))
+__global__ void __launch_bounds__(Cfg::THREADS, (Cfg::THREADS <= 128 ? Cfg::MINB : 1))
 lfa_bwd_kernel(const float* __restrict__ x, const float* __restrict__ pos, const int32_t* __restrict__ nbr,
                const float* __restrict__ enc_w, const float* __restrict__ enc_b,
                const float* __restrict__ att_wt, const float* __restrict__ att_w,
@@ -400,6 +415,12 @@ lfa_bwd_kernel(const float* __restrict__ x, const float* __restrict__ pos, const
   for (int p = 0; p < DWP; ++p)
 #pragma unroll
     for (int t = 0; t < 16; ++t) dw[p][t] = 0.f;
+  constexpr bool DWC = !SPLIT_DW && Plan::DW_BY_CENTRE;
+  float dwc[DWC ? CW : 1][DWC ? C : 1];
+#pragma unroll
+  for (int cw = 0; cw < (DWC ? CW : 1); ++cw)
+#pragma unroll
+    for (int m = 0; m < (DWC ? C : 1); ++m) dwc[cw][m] = 0.f;
   constexpr int GEW = Plan::GE_IN_REGS ? CW : 1;
   float ge_reg[GEW][8];
 #pragma unroll
@@ -474,6 +495,21 @@ lfa_bwd_kernel(const float* __restrict__ x, const float* __restrict__ pos, const
           }
         }
         store_vec<CW>(DAg + k * C + col0, da);
+        if constexpr (DWC) {
+          if (k < deg) {
+#pragma unroll
+            for (int m4 = 0; m4 < C / 4; ++m4) {
+              const float4 fr = *reinterpret_cast<const float4*>(Fg + k * C + m4 * 4);  // broadcast within the centre
+#pragma unroll
+              for (int cw = 0; cw < CW; ++cw) {
+                dwc[cw][m4 * 4 + 0] = fmaf(da[cw], fr.x, dwc[cw][m4 * 4 + 0]);
+                dwc[cw][m4 * 4 + 1] = fmaf(da[cw], fr.y, dwc[cw][m4 * 4 + 1]);
+                dwc[cw][m4 * 4 + 2] = fmaf(da[cw], fr.z, dwc[cw][m4 * 4 + 2]);
+                dwc[cw][m4 * 4 + 3] = fmaf(da[cw], fr.w, dwc[cw][m4 * 4 + 3]);
+              }
+            }
+          }
+        }
         if constexpr (SPLIT_DW) {
           if (i < n) {  // stream the edge rows out for the split-K dW GEMM
             const int64_t row = (i * KT + k) * C + col0;
@@ -528,7 +564,7 @@ lfa_bwd_kernel(const float* __restrict__ x, const float* __restrict__ pos, const
       }
     }
 
-    if constexpr (!SPLIT_DW) {
+    if constexpr (!SPLIT_DW && !DWC) {
       // GEMM3: dW[n][m] += sum_e DA[e][n] F[e][m], 4x4 register blocks carried across tiles
 #pragma unroll
       for (int pass = 0; pass < Plan::PASSES; ++pass) {
@@ -553,7 +589,20 @@ lfa_bwd_kernel(const float* __restrict__ x, const float* __restrict__ pos, const
   }
 
   // flush the per-CTA partial gradients
-  if constexpr (!SPLIT_DW) {
+  if constexpr (DWC) {
+    // reduce the per-thread dW rows over the centres of the CTA in shared memory (the F tile is free now)
+    float* DWS = F;  // [C][C]
+    __syncthreads();
+    for (int t = tid; t < C * C; t += THREADS) DWS[t] = 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int cw = 0; cw < CW; ++cw)
+#pragma unroll
+      for (int m = 0; m < C; ++m) atomicAdd(&DWS[(col0 + cw) * C + m], dwc[cw][m]);
+    __syncthreads();
+    for (int t = tid; t < C * C; t += THREADS) atomicAdd(grad_att_w + t, DWS[t]);
+  }
+  if constexpr (!SPLIT_DW && !DWC) {
 #pragma unroll
     for (int pass = 0; pass < Plan::PASSES; ++pass) {
       const int ob = (Plan::SLICES > 1) ? (tid / Plan::SLICES) : (pass * THREADS + tid);
@@ -674,10 +723,10 @@ extern "C" int b200_edge_moments(const float* pos, const int32_t* nbr, int64_t n
 // X(C, KT, CW, TC[, SPLIT_DW]): THREADS = TC * C / CW.  Small tiles + CW = 4 keep registers near 128 and shared
 // memory near 33 KB (fwd) / 66 KB (bwd) so that 3-4 CTAs share an SM.
 #define B200_LFA_FWD_CASES(X) \
-  X(8, 16, 2, 32) X(16, 16, 4, 32) X(32, 16, 4, 16) X(64, 16, 4, 8) X(128, 16, 4, 4) X(256, 16, 4, 2) \
+  X(8, 16, 2, 32) X(16, 16, 4, 32) X(32, 16, 2, 8) X(64, 16, 4, 8) X(128, 16, 4, 4) X(256, 16, 4, 2) \
   X(8, 32, 2, 32) X(16, 32, 4, 32) X(32, 32, 4, 16) X(64, 32, 4, 8) X(128, 32, 4, 4) X(256, 32, 4, 2)
 #define B200_LFA_BWD_CASES(X) \
-  X(8, 16, 2, 32, false) X(16, 16, 4, 32, false) X(32, 16, 4, 16, false) \
+  X(8, 16, 2, 32, false) X(16, 16, 2, 16, false, 3) X(32, 16, 2, 8, false, 3) \
   X(64, 16, 4, 8, true) X(128, 16, 4, 4, true) X(256, 16, 4, 2, true) \
   X(8, 32, 2, 32, false) X(16, 32, 4, 32, false) X(32, 32, 4, 16, false) \
   X(64, 32, 4, 4, true) X(128, 32, 4, 2, true) X(256, 32, 4, 2, true)
@@ -722,9 +771,9 @@ extern "C" int b200_lfa_bwd(const float* x, const float* pos, const int32_t* nbr
                (long long)b200_lfa_bwd_workspace_bytes(n, c, kt));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   float* ws = static_cast<float*>(workspace);
-#define X(C_, KT_, CW_, TC_, SPLIT_)                                                                       \
+#define X(C_, KT_, CW_, TC_, SPLIT_, ...)                                                                  \
   if (c == C_ && kt == KT_)                                                                                \
-    return launch_lfa_bwd<LfaCfg<C_, KT_, CW_, TC_>, SPLIT_>(x, pos, nbr, enc_w, enc_b, att_wt, att_w, grad_out, \
+    return launch_lfa_bwd<LfaCfg<C_, KT_, CW_, TC_, ##__VA_ARGS__>, SPLIT_>(x, pos, nbr, enc_w, enc_b, att_wt, att_w, grad_out, \
                                                              grad_x, grad_enc_w, grad_enc_b, grad_att_w, ws, n, st);
   B200_LFA_BWD_CASES(X)
 #undef X

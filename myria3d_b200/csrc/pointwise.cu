@@ -531,20 +531,25 @@ __global__ void bn_finalize_kernel(const double* __restrict__ colstats, int num_
                                    float momentum, float eps, float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
                                    float* __restrict__ invstd_out, int c) {
   if (blockIdx.x == 0 && threadIdx.x == 0 && colstats && num_batches_tracked) *num_batches_tracked += 1;
-  // one warp per channel: lanes stride over the partial rows, then a shuffle reduction
-  const int lane = threadIdx.x & 31;
-  const int warps = (blockDim.x >> 5) * gridDim.x;
-  for (int ch = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); ch < c; ch += warps) {
+  // one CTA per channel: 128 threads stride over the partial rows (up to 1600 of them at level 0), then reduce
+  __shared__ double sh1[4], sh2[4];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int ch = blockIdx.x; ch < c; ch += gridDim.x) {
     double mean, var;
     if (colstats) {
       double s1 = 0.0, s2 = 0.0;
-      for (int p = lane; p < num_partials; p += 32) {
+      for (int p = threadIdx.x; p < num_partials; p += blockDim.x) {
         s1 += colstats[(int64_t)p * 2 * c + ch];
         s2 += colstats[(int64_t)p * 2 * c + c + ch];
       }
       s1 = warp_sum(s1);
       s2 = warp_sum(s2);
-      if (lane != 0) continue;
+      __syncthreads();  // sh1/sh2 of the previous channel have been consumed
+      if (lane == 0) sh1[warp] = s1, sh2[warp] = s2;
+      __syncthreads();
+      if (threadIdx.x != 0) continue;
+      s1 = sh1[0] + sh1[1] + sh1[2] + sh1[3];
+      s2 = sh2[0] + sh2[1] + sh2[2] + sh2[3];
       mean = s1 / (double)count;
       var = s2 / (double)count - mean * mean;
       if (var < 0.0) var = 0.0;
@@ -554,7 +559,7 @@ __global__ void bn_finalize_kernel(const double* __restrict__ colstats, int num_
         running_var[ch] = (float)((1.0 - (double)momentum) * (double)running_var[ch] + (double)momentum * unbiased);
       }
     } else {
-      if (lane != 0) continue;
+      if (threadIdx.x != 0) continue;
       mean = (double)running_mean[ch];
       var = (double)running_var[ch];
     }
@@ -845,7 +850,7 @@ extern "C" int b200_bn_finalize(const double* colstats, int32_t num_partials, in
   B200_REQUIRE((running_mean == nullptr) == (running_var == nullptr), B200_E_INVALID,
                "b200_bn_finalize: running_mean / running_var must come together");
   B200_REQUIRE(!colstats || num_partials >= 1, B200_E_INVALID, "b200_bn_finalize: num_partials must be >= 1");
-  bn_finalize_kernel<<<(unsigned)ceil_div(c, 4), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+  bn_finalize_kernel<<<(unsigned)c, 128, 0, static_cast<cudaStream_t>(stream)>>>(
       colstats, num_partials, count, gamma, beta, running_mean, running_var, num_batches_tracked, momentum, eps, scale, shift, mean,
       invstd, c);
   B200_CHECK_LAUNCH("bn_finalize_kernel");
