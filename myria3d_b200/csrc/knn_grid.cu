@@ -12,11 +12,12 @@
 //   2. grid_count  : cell of every point (stored) + per-cell histogram (atomics)
 //   3. grid_scan   : one CTA per cloud -> exclusive scan of the G*G counters (cell start offsets)
 //   4. grid_scatter: counting-sort scatter into cell order as float4 (x, y, z, original index bits)
-//   5. knn_grid    : one thread per query walks square rings of cells around its own cell; a ring row is
-//                    one contiguous run of the sorted array.  The search stops when the k-th distance is
-//                    smaller than the distance to the border of the visited block (conservative, with
-//                    slack for the float rounding of the cell assignment).  For self-queries the threads
-//                    follow the cell order, so a warp's lanes read (almost) the same runs.
+//   5. knn_grid    : square rings of cells around the query's cell are visited until the k-th distance is smaller
+//                    than the distance to the border of the visited block (conservative, with slack for the
+//                    float rounding of the cell assignment); a ring row is one contiguous run of the sorted
+//                    array.  One thread per query; for self-queries (kNN graph) the threads follow the cell order so that
+//                    a warp's lanes read (almost) the same runs.  (A warp-cooperative walk of the union block was
+//                    measured: no gain, the lane-private top-k insertion dominates either way.)
 //
 // Insertion is lexicographic on (distance, index): the result does not depend on the visiting order,
 // hence not on the (atomic, non-deterministic) order of points inside a cell.

@@ -740,6 +740,10 @@ extern "C" int b200_lfa_fwd(const float* x, const float* pos, const int32_t* nbr
                "b200_lfa_fwd: x, att_wt and out must be 16-byte aligned");
   if (n <= 0) return B200_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  {  // c in {64, 128}: attention contraction on the tensor cores (lfa_tc.cu)
+    const int rc = lfa_tc_fwd_dispatch(x, pos, nbr, enc_w, enc_b, att_wt, out, n, c, kt, st);
+    if (rc != B200_E_UNSUPPORTED) return rc;
+  }
 #define X(C_, KT_, CW_, TC_) \
   if (c == C_ && kt == KT_) return launch_lfa_fwd<LfaCfg<C_, KT_, CW_, TC_>>(x, pos, nbr, enc_w, enc_b, att_wt, out, n, st);
   B200_LFA_FWD_CASES(X)

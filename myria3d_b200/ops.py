@@ -81,7 +81,7 @@ def table_width(k: int) -> int:
 
 
 # ------------------------------------------------------------------------------------------- kNN
-GRID_KNN_MIN_POINTS = 512  # clouds at least this large use the bucket-grid search
+GRID_KNN_MIN_POINTS = 1024  # clouds at least this large use the bucket-grid search (measured crossover)
 
 
 def knn(pos_x: Tensor, ptr_x: Tensor, pos_y: Tensor, ptr_y: Tensor, k: int, max_queries_per_cloud: int,

@@ -219,6 +219,33 @@ def test_lfa_module_parity(lib, c, k, training):
             assert_close(b, dict(ref.named_buffers())[name], atol=1e-5, rtol=1e-5, what=name)
 
 
+@pytest.mark.parametrize("c", [64, 128])
+def test_lfa_forward_tensor_core_path(lib, c, monkeypatch):
+    """The tcgen05 (3xTF32, TMEM) fused LFA forward (lfa_tc.cu, opt-in) gives the same pooled features as the FMA
+    kernel -- fp32-grade: rel 2e-5 -- on ragged clouds (degrees < K, partial last tile)."""
+    from myria3d_b200 import ops
+    from myria3d_b200.randla_net import _Level
+
+    sizes = [530, 9, 1, 77]
+    _, pos, _, ptr = rand_cloud(sizes, seed=c)
+    n = sum(sizes)
+    g = torch.Generator().manual_seed(c + 1)
+    x = torch.randn(n, c // 2, generator=g).to(DEV)
+    enc_w = (torch.randn(c // 2, 7, generator=g) * 0.5).to(DEV)
+    enc_b = (torch.randn(c // 2, generator=g) * 0.1).to(DEV)
+    att_w = (torch.randn(c, c, generator=g) / c ** 0.5).to(DEV)
+    lvl = _Level(ptr.tolist(), torch.device(DEV))
+    posd = pos.to(DEV)
+    nbr, _ = ops.knn(posd, lvl.ptr, posd, lvl.ptr, 16, lvl.max_n, kt=16, want_dist=False)
+    monkeypatch.delenv("B200_LFA_TCGEN05", raising=False)
+    ref = ops.lfa_attentive_pool(x, posd, nbr, enc_w, enc_b, att_w)
+    monkeypatch.setenv("B200_LFA_TCGEN05", "1")
+    out = ops.lfa_attentive_pool(x, posd, nbr, enc_w, enc_b, att_w)
+    torch.cuda.synchronize()
+    assert rel_err(out, ref) < 2e-5, rel_err(out, ref)
+    assert_close(out, ref, atol=2e-5 * float(ref.abs().max()), what="tcgen05 LFA forward")
+
+
 # ------------------------------------------------------------------------------ per-point layers
 def test_linear_stats_cancellation(lib):
     """|mean| >> std: the fp64 statistics epilogue must still resolve the variance (2-row batches of
