@@ -176,6 +176,44 @@ def algorithmic_bytes(name: str, a):
     return 0
 
 
+def algorithmic_flops(name: str, a):
+    """fp32 flops of one library call in the reference formulation (SURVEY.md 8d: LFA per centre K*(2*10*c/2 + 2c^2) forward;
+    backward = score recompute + dF + dW contractions (6c^2 per edge) + encoder forward/backward)."""
+    if name == "b200_lfa_fwd":
+        n, c, kt = a
+        return n * kt * (10 * c + 2 * c * c)
+    if name == "b200_lfa_bwd":
+        _ws, n, c, kt = a
+        return n * kt * (20 * c + 6 * c * c)
+    if name in ("b200_linear_fwd", "b200_linear_bwd_input"):
+        _l1, c1, _l2, c2, n, cout = a
+        return 2 * n * (c1 + c2) * cout
+    if name == "b200_linear_bwd_weight":
+        _l1, c1, _l2, c2, _ws, n, cout = a
+        return 2 * n * (c1 + c2) * cout
+    return 0
+
+
+def ncu_traffic(name: str, a):
+    """dram bytes per launch of this kernel/shape from the committed single-kernel ncu capture, else None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")) as f:
+            entries = json.load(f)["entries"]
+    except Exception:
+        return None, None
+    named = {}
+    if name == "b200_lfa_bwd":
+        named = dict(zip(("ws", "n", "c", "kt"), a))
+    elif name == "b200_lfa_fwd":
+        named = dict(zip(("n", "c", "kt"), a))
+    elif name == "b200_knn_grid":
+        named = dict(zip(("nx", "ny", "clouds", "mx", "my", "k", "kt", "ws"), a))
+    for e in entries:
+        if e["kernel"] == name and all(named.get(k) == v for k, v in e["match"].items()):
+            return int(e["dram_bytes"]), e["source"]
+    return None, None
+
+
 def kernel_table(records):
     groups = {}
     for name, ints, ms in records:
@@ -376,7 +414,12 @@ def run_b200(args):
 
     launches0 = launches_now()
     barrier()
+    ncu_range = os.environ.get("B200_NCU_RANGE") == "1"  # `ncu --profile-from-start off`: capture the timed steps only
+    if ncu_range:
+        torch.cuda.profiler.start()
     total_ms = timed("resident", args.steps)
+    if ncu_range:
+        torch.cuda.profiler.stop()
     barrier()
     launches = (launches_now() - launches0) // max(args.steps, 1)
     total_ms = max_over_ranks(total_ms)
@@ -414,9 +457,19 @@ def run_b200(args):
         if table:
             top = table[0]
             lib_ms = sum(g["ms"] for g in table)
+            traffic, traffic_src = ncu_traffic(top["name"], tuple(top["args"]))
+            flops = algorithmic_flops(top["name"], tuple(top["args"]))
+            sm_max = (clocks or {}).get("sm_max_mhz") or 1965
+            fma_peak = torch.cuda.get_device_properties(dev).multi_processor_count * 128 * 2 * sm_max * 1e6 / 1e12
+            tfs = flops / (top["ms_per_launch"] * 1e-3) / 1e12
             roof = {"bound": "hbm", "kernel": top["name"], "kernel_args": top["args"],
                     "achieved": top["gbs"], "peak": peak, "unit": "GB/s", "frac": top["gbs"] / peak,
-                    "traffic": None, "peak_source": peak_src, "launch_ms": top["ms_per_launch"],
+                    "traffic": traffic, "traffic_source": traffic_src,
+                    # the same launch against the fp32 FMA pipe (SMs x 128 lanes x 2 x max clock): the fused LFA kernels are
+                    # ALU-bound long before they are HBM-bound
+                    "fp32_fma": {"flops": flops, "achieved": tfs, "peak": fma_peak, "unit": "TFLOP/s",
+                                 "frac": tfs / fma_peak if fma_peak else None},
+                    "peak_source": peak_src, "launch_ms": top["ms_per_launch"],
                     "share_of_library_time": top["ms"] / lib_ms if lib_ms > 0 else None,
                     "library_ms_per_step": lib_ms}
             report = args.kernel_report

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define B200_ABI_VERSION 2
+#define B200_ABI_VERSION 3
 
 #define B200_OK 0
 #define B200_E_INVALID 1     /* bad argument (null pointer, unsupported size/alignment) */
@@ -233,6 +233,20 @@ int b200_affine_act_bwd_apply(const float* grad_out, const float* out, float slo
  * CUDA-graph capturable.  All buffers 16-byte aligned. */
 int b200_adam_flat(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
                    float lr, float beta1, float beta2, float eps, int64_t* step, void* stream);
+
+/* ------------------------------------------------------- sliding-window stitch ---
+ * b200_stitch_segment_sum replaces torch_scatter.scatter_sum(logits, idx_in_full_cloud, out=zeros(nb_points, C))
+ * (myria3d/models/interpolation.py:113-116).  `order` is a STABLE argsort of the destination indices and
+ * `sorted_idx = idx[order]`; every destination row is summed sequentially in input order (bit-identical to the
+ * reference's CPU scatter, deterministic, no atomics).  `out` is pre-zeroed by the caller; rows without a
+ * prediction stay zero.
+ * b200_stitch_finalize replaces reduced_logits[idx] (:121), Softmax(dim=1) (:142), argmax (:145) and
+ * Categorical(probs).entropy() (:166) in one pass; logits / probas / preds / entropy may each be NULL.
+ * c <= 32 classes. */
+int b200_stitch_segment_sum(const float* rows, const int64_t* order, const int64_t* sorted_idx, float* out,
+                            int64_t m, int32_t c, int64_t nb_points, void* stream);
+int b200_stitch_finalize(const float* reduced, const int64_t* idx, float* logits, float* probas, int64_t* preds,
+                         float* entropy, int64_t m, int32_t c, void* stream);
 
 /* ------------------------------------------------------- tcgen05 self-test --------------
  * d[128, n] = a[128, k] * b[n, k]^T on the 5th-generation tensor cores (tcgen05.mma kind::tf32, TMEM

@@ -31,6 +31,8 @@ _SIGNATURES = {
     "b200_lfa_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int64, c_int32, c_int32, _P]),
     "b200_gather_rows": (c_int, [_P, _P, _P, c_int64, c_int32, _P]),
     "b200_scatter_rows_add": (c_int, [_P, _P, _P, c_int64, c_int32, _P]),
+    "b200_stitch_segment_sum": (c_int, [_P, _P, _P, _P, c_int64, c_int32, c_int64, _P]),
+    "b200_stitch_finalize": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int32, _P]),
     "b200_knn_interp_fwd": (c_int, [_P, _P, _P, _P, c_int64, c_int32, c_int32, c_int32, c_int64, _P]),
     "b200_knn_interp_bwd": (c_int, [_P, c_int64, _P, _P, _P, c_int64, c_int32, c_int32, c_int32, _P]),
     "b200_linear_fwd": (c_int, [_P, c_int64, c_int32, _P, c_int64, c_int32, _P, _P, _P, c_int64, c_int32, _P, _P]),
@@ -49,7 +51,7 @@ _SIGNATURES = {
     ),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 _lib = None
 

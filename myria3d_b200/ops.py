@@ -441,3 +441,40 @@ def bn_act(y: Tensor, stats: Optional[Tensor], bn: torch.nn.BatchNorm1d, slope: 
         args2 = (y2, stats2, bn2.weight, bn2.bias, rm2, rv2, bn2.num_batches_tracked)
     return _BNAct.apply(y, stats, bn.weight, bn.bias, rm1, rv1, bn.num_batches_tracked, *args2, float(slope),
                         float(bn.momentum), float(bn.eps))
+
+
+# ------------------------------------------------------------------------------ sliding-window stitch
+def stitch_scatter_sum(logits: Tensor, idx: Tensor, nb_points: int) -> Tensor:
+    """``scatter_sum(logits, idx, out=zeros(nb_points, C))`` (``interpolation.py:113-116``), summing the predictions of
+    one point in input order (bit-identical to the reference's CPU scatter; deterministic)."""
+    _need_cuda(logits, idx)
+    logits = _f32c(logits)
+    idx = idx.to(torch.int64).contiguous()
+    m, c = logits.shape
+    if idx.numel() != m:
+        raise ValueError(f"stitch_scatter_sum: {idx.numel()} indices for {m} rows")
+    if m and (int(idx.min()) < 0 or int(idx.max()) >= nb_points):
+        raise IndexError(f"stitch_scatter_sum: index out of range for {nb_points} points")
+    out = torch.zeros(nb_points, c, dtype=torch.float32, device=logits.device)
+    if m == 0:
+        return out
+    sorted_idx, order = torch.sort(idx, stable=True)
+    _call("b200_stitch_segment_sum", _p(logits), _p(order), _p(sorted_idx), _p(out), m, c, nb_points, _stream())
+    return out
+
+
+def stitch_finalize(reduced: Tensor, idx: Tensor, want_logits: bool = True):
+    """``reduced[idx]`` + softmax + argmax + Shannon entropy (``interpolation.py:121,142-166``) in one kernel.
+    Returns ``(logits | None, probas, preds int64, entropy)``, each with ``len(idx)`` rows."""
+    _need_cuda(reduced, idx)
+    reduced = _f32c(reduced)
+    idx = idx.to(torch.int64).contiguous()
+    m, c = idx.numel(), reduced.shape[1]
+    dev = reduced.device
+    logits = torch.empty(m, c, dtype=torch.float32, device=dev) if want_logits else None
+    probas = torch.empty(m, c, dtype=torch.float32, device=dev)
+    preds = torch.empty(m, dtype=torch.int64, device=dev)
+    entropy = torch.empty(m, dtype=torch.float32, device=dev)
+    if m:
+        _call("b200_stitch_finalize", _p(reduced), _p(idx), _p(logits), _p(probas), _p(preds), _p(entropy), m, c, _stream())
+    return logits, probas, preds, entropy

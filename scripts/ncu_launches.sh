@@ -1,9 +1,11 @@
 #!/bin/bash
-# ncu launch list (device time of EVERY kernel, torch's included) of one eager bench run.
+# ncu launch list (device time of EVERY kernel, torch's included) of ONE timed bench step (graph replay).
+# bench.py brackets the timed region with cudaProfilerStart/Stop when B200_NCU_RANGE=1, so warm-up, graph capture and the
+# per-kernel event pass are not replayed under ncu (~0.4 s per profiled launch: ~500 launches -> ~4 min).
 # Usage (on the GPU box, through gpurun): bash scripts/ncu_launches.sh <tag>
 tag=${1:-r1}
-ncu --metrics gpu__time_duration.sum --clock-control none -c 40000 --csv \
-    --log-file gpurun_out/launches_${tag}.csv \
-    python bench.py --eager --steps 2 --warmup 3 --profile-steps 0 --no-cpu-baseline > gpurun_out/launches_${tag}.bench.log 2>&1
-python scripts/summarize_launches.py gpurun_out/launches_${tag}.csv > gpurun_out/launches_${tag}.summary.txt
-tail -60 gpurun_out/launches_${tag}.summary.txt
+B200_NCU_RANGE=1 timeout 900 ncu --profile-from-start off --graph-profiling node --metrics gpu__time_duration.sum \
+    --clock-control none -c 3000 --csv --log-file gpurun_out/launches_${tag}.csv \
+    python bench.py --steps 1 --warmup 3 --profile-steps 0 --no-cpu-baseline > gpurun_out/launches_${tag}.bench.log 2>&1
+python scripts/summarize_launches.py gpurun_out/launches_${tag}.csv --all > gpurun_out/launches_${tag}.summary.txt
+head -50 gpurun_out/launches_${tag}.summary.txt

@@ -33,7 +33,9 @@ for i, (_, name, _) in enumerate(rows):
     elif "knn_kernel" in name:
         last = last  # same step
 print("step starts at launch indices", starts)
-if len(starts) >= 2:
+if "--all" in sys.argv:  # the capture is already exactly one step (B200_NCU_RANGE=1 / --profile-from-start off)
+    seg = rows
+elif len(starts) >= 2:
     seg = rows[starts[-2]:starts[-1]]
 else:
     seg = rows
@@ -45,7 +47,7 @@ for _, name, ns in seg:
     a[1] += ns
 tot = sum(v[1] for v in agg.values())
 print(f"one step: {len(seg)} launches, {tot/1e6:.3f} ms of kernel time")
-ours = sum(v[1] for k, v in agg.items() if "_kernel" in k and ("lfa" in k or "knn" in k or "linear" in k or "affine" in k or "bn_finalize" in k or "rows" in k or "interp" in k or "moments" in k))
+ours = sum(v[1] for k, v in agg.items() if "_kernel" in k and ("lfa" in k or "knn" in k or "linear" in k or "affine" in k or "bn_finalize" in k or "rows" in k or "interp" in k or "moments" in k or "tc_" in k or "tn_skinny" in k or "grid_" in k or "fold" in k or "adam" in k or "increment" in k))
 print(f"libb200randla kernels: {ours/1e6:.3f} ms ({100*ours/tot:.1f} %), other (torch) kernels: {(tot-ours)/1e6:.3f} ms")
 for k, (n, ns) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:70]:
     print(f"{ns/1e3:10.1f} us {100*ns/tot:5.1f}%  n={n:4d}  {k}")

@@ -2,6 +2,8 @@
 structural pins (shipped checkpoint, shape tests).  No GPU, no CUDA library calls."""
 import os
 
+import numpy as np
+
 import pytest
 import torch
 import torch.nn.functional as F
@@ -144,3 +146,23 @@ def test_block1_net_config_a_runs():
     loss = F.cross_entropy(out, y)
     loss.backward()
     assert out.shape == (8192, 6) and torch.isfinite(loss)
+
+
+def test_stitch_oracle_scatter_order_and_entropy():
+    """interpolation.py:113-121,142-166: scatter_add_ on CPU sums in input order (== explicit loop, bit for bit) and the
+    entropy restatement equals -sum(p log p) for unsaturated probabilities."""
+    from oracle import stitch_oracle as SO
+
+    g = torch.Generator().manual_seed(3)
+    logits = torch.randn(4000, 7, generator=g) * 4
+    idx = torch.randint(0, 900, (4000,), generator=g)
+    a = SO.scatter_sum_rows(logits, idx, 1000)
+    b = SO.scatter_sum_rows_loop(logits, idx.tolist(), 1000)
+    assert torch.equal(a, b)
+    assert not a[900:].any()  # points without a prediction keep zero logits
+    out, idx_np = SO.reduce_predictions([logits[:2500], logits[2500:]], [idx[:2500].numpy(), idx[2500:].numpy()], 1000,
+                                        {1: "a", 2: "b", 6: "c", 9: "d", 17: "e", 64: "f", 65: "g"})
+    p = out["probas"].double()
+    torch.testing.assert_close(out["entropy"].double(), -(p * p.clamp_min(1e-30).log()).sum(1), rtol=1e-4, atol=1e-5)
+    assert set(np.unique(out["preds"])) <= {1, 2, 6, 9, 17, 64, 65}
+    assert torch.equal(out["logits"], a[idx_np])
