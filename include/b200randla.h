@@ -94,7 +94,8 @@ int b200_edge_moments(const float* pos, const int32_t* nbr, int64_t n, int32_t k
  * Training also updates running_mean / running_var (unbiased variance) and increments
  * *num_batches_tracked (int64, may be NULL) exactly like torch.nn.BatchNorm1d.
  * The backward returns the exact train-mode gradients through the batch statistics:
- *   grad_w [h,10], grad_b [h] (may be NULL; identically 0 in training), grad_gamma, grad_beta (written). */
+ *   grad_w [h,10], grad_b [h] (may be NULL; identically 0 in training), grad_gamma, grad_beta: written when
+ *   accumulate == 0, added to (+=) when accumulate != 0 (the buffers are then the parameters' .grad). */
 int b200_encoder_fold_fwd(const float* w, const float* b, const float* gamma, const float* beta,
                           const double* moments, float* running_mean, float* running_var,
                           int64_t* num_batches_tracked, float momentum, float eps,
@@ -103,7 +104,7 @@ int b200_encoder_fold_bwd(const float* w, const float* b, const float* gamma, co
                           const float* running_mean, const float* running_var, float eps,
                           const float* g_enc_w, const float* g_enc_b,
                           float* grad_w, float* grad_b, float* grad_gamma, float* grad_beta,
-                          int32_t h, void* stream);
+                          int32_t h, int32_t accumulate, void* stream);
 
 /* Fused forward.  c = channels of the LFA (x has h = c/2 features).
  *   x       fp32 [n, h]        pos fp32 [n, 3]      nbr int32 [n, kt]
@@ -214,7 +215,8 @@ int b200_affine_act_bwd_reduce(const float* grad_out, const float* out, float sl
                                int64_t n, int32_t c, void* stream);
 /* Backward, pass 2 (train-mode BatchNorm): with xhat = (y - mean) * invstd,
  *   grad_y = gamma*invstd * (g - red[0:c]/n - xhat * red[c:2c]/n),
- *   grad_gamma = red[c:2c], grad_beta = red[0:c]  (written, not accumulated).
+ *   grad_gamma += red[c:2c], grad_beta += red[0:c]  (ACCUMULATED when the pointers are given: pass the parameters'
+ *   .grad buffers, or zero-filled temporaries).
  * Eval mode / plain affine (red == NULL): grad_y = g * scale.
  * grad_y2 (second branch) is produced when y2 != NULL. */
 int b200_affine_act_bwd_apply(const float* grad_out, const float* out, float slope,
@@ -225,6 +227,19 @@ int b200_affine_act_bwd_apply(const float* grad_out, const float* out, float slo
                               const double* red2, const float* scale2, float* grad_y2,
                               float* grad_gamma2, float* grad_beta2,
                               int64_t n, int32_t c, void* stream);
+
+/* ------------------------------------------------------- loss --------------------------
+ * torch.nn.CrossEntropyLoss(weight | NULL, ignore_index, label_smoothing=0, reduction="mean") on [n, c] logits and
+ * int64 targets (configs/model/criterion/*.yaml; models/model.py:117-118,135-136,152-153); c <= 32.
+ *   fwd: acc (fp64 [2]) and counter (uint32 [1]) are zero-filled scratch; loss_out fp32 [2] = {mean loss, sum of the
+ *        weights of the rows that count} (the second value feeds the backward).  0 counted rows -> NaN like torch; a
+ *        target outside [0, c) other than ignore_index also yields NaN (torch: device-side assert).
+ *   bwd: grad_logits [n, c] = *grad_loss * w[t] * (softmax(x) - onehot(t)) / loss_out[1]; ignored rows get 0. */
+int b200_cross_entropy_fwd(const float* logits, const int64_t* target, const float* weight, int64_t n, int32_t c,
+                           int64_t ignore_index, double* acc, uint32_t* counter, float* loss_out, void* stream);
+int b200_cross_entropy_bwd(const float* logits, const int64_t* target, const float* weight, int64_t n, int32_t c,
+                           int64_t ignore_index, const float* loss_and_wsum, const float* grad_loss,
+                           float* grad_logits, void* stream);
 
 /* ------------------------------------------------------- optimizer ----------------------
  * One Adam update over FLAT fp32 buffers (parameters, gradients, first and second moments), the arithmetic of

@@ -42,7 +42,9 @@ _SIGNATURES = {
     "b200_linear_fwd_num_stat_partials": (c_int64, [c_int64, c_int32, c_int32, c_int32]),
     "b200_bn_finalize": (c_int, [_P, c_int32, c_int64, _P, _P, _P, _P, _P, c_float, c_float, _P, _P, _P, _P, c_int32, _P]),
     "b200_encoder_fold_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_float, c_float, _P, _P, c_int32, _P]),
-    "b200_encoder_fold_bwd": (c_int, [_P, _P, _P, _P, _P, _P, c_float, _P, _P, _P, _P, _P, _P, c_int32, _P]),
+    "b200_encoder_fold_bwd": (c_int, [_P, _P, _P, _P, _P, _P, c_float, _P, _P, _P, _P, _P, _P, c_int32, c_int32, _P]),
+    "b200_cross_entropy_fwd": (c_int, [_P, _P, _P, c_int64, c_int32, c_int64, _P, _P, _P, _P]),
+    "b200_cross_entropy_bwd": (c_int, [_P, _P, _P, c_int64, c_int32, c_int64, _P, _P, _P, _P]),
     "b200_affine_act_fwd": (c_int, [_P, _P, _P, _P, _P, _P, c_float, _P, c_int64, c_int32, _P]),
     "b200_affine_act_bwd_reduce": (c_int, [_P, _P, c_float, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int32, _P]),
     "b200_affine_act_bwd_apply": (

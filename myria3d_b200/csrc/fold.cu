@@ -83,7 +83,8 @@ __global__ void encoder_fold_bwd_kernel(const float* __restrict__ w, const float
                                         const float* __restrict__ running_mean, const float* __restrict__ running_var,
                                         float eps, const float* __restrict__ g_enc_w, const float* __restrict__ g_enc_b,
                                         float* __restrict__ grad_w, float* __restrict__ grad_b,
-                                        float* __restrict__ grad_gamma, float* __restrict__ grad_beta, int h) {
+                                        float* __restrict__ grad_gamma, float* __restrict__ grad_beta, int h,
+                                        int accumulate) {
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= h) return;
   FoldRow R;
@@ -110,13 +111,22 @@ __global__ void encoder_fold_bwd_kernel(const float* __restrict__ w, const float
     if (mom) dwq[t] += -gc * s * R.mu[t] + 2.0 * dv * R.cw[t];
   }
   float* gw = grad_w + m * 10;
-  gw[0] = (float)dwq[0], gw[1] = (float)dwq[1], gw[2] = (float)dwq[2];
-  gw[3] = (float)dwq[3], gw[4] = (float)dwq[4], gw[5] = (float)dwq[5];
-  gw[6] = (float)(dwq[3] - dwq[0]), gw[7] = (float)(dwq[4] - dwq[1]), gw[8] = (float)(dwq[5] - dwq[2]);
-  gw[9] = (float)dwq[6];
-  if (grad_b) grad_b[m] = mom ? 0.f : (float)(gc * s);  // train mode: the bias cancels inside BatchNorm
-  grad_gamma[m] = (float)(ds * r);
-  grad_beta[m] = (float)gc;
+  const float gwv[10] = {(float)dwq[0], (float)dwq[1], (float)dwq[2], (float)dwq[3], (float)dwq[4], (float)dwq[5],
+                         (float)(dwq[3] - dwq[0]), (float)(dwq[4] - dwq[1]), (float)(dwq[5] - dwq[2]), (float)dwq[6]};
+  const float gbv = mom ? 0.f : (float)(gc * s);  // train mode: the bias cancels inside BatchNorm
+  if (accumulate) {  // outputs are the parameters' .grad buffers
+#pragma unroll
+    for (int j = 0; j < 10; ++j) gw[j] += gwv[j];
+    if (grad_b) grad_b[m] += gbv;
+    grad_gamma[m] += (float)(ds * r);
+    grad_beta[m] += (float)gc;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 10; ++j) gw[j] = gwv[j];
+    if (grad_b) grad_b[m] = gbv;
+    grad_gamma[m] = (float)(ds * r);
+    grad_beta[m] = (float)gc;
+  }
 }
 
 }  // namespace b200
@@ -141,13 +151,15 @@ extern "C" int b200_encoder_fold_fwd(const float* w, const float* b, const float
 extern "C" int b200_encoder_fold_bwd(const float* w, const float* b, const float* gamma, const double* moments,
                                      const float* running_mean, const float* running_var, float eps,
                                      const float* g_enc_w, const float* g_enc_b, float* grad_w, float* grad_b,
-                                     float* grad_gamma, float* grad_beta, int32_t h, void* stream) {
+                                     float* grad_gamma, float* grad_beta, int32_t h, int32_t accumulate,
+                                     void* stream) {
   B200_REQUIRE(w && gamma && g_enc_w && g_enc_b && grad_w && grad_gamma && grad_beta && h > 0, B200_E_INVALID,
                "b200_encoder_fold_bwd: null pointer / h <= 0");
   B200_REQUIRE(moments || (running_mean && running_var), B200_E_INVALID,
                "b200_encoder_fold_bwd: eval mode needs running statistics");
   encoder_fold_bwd_kernel<<<(unsigned)ceil_div(h, 64), 64, 0, static_cast<cudaStream_t>(stream)>>>(
-      w, b, gamma, moments, running_mean, running_var, eps, g_enc_w, g_enc_b, grad_w, grad_b, grad_gamma, grad_beta, h);
+      w, b, gamma, moments, running_mean, running_var, eps, g_enc_w, g_enc_b, grad_w, grad_b, grad_gamma, grad_beta, h,
+      accumulate);
   B200_CHECK_LAUNCH("encoder_fold_bwd_kernel");
   return B200_OK;
 }

@@ -671,16 +671,17 @@ affine_act_bwd_apply_kernel(const float* __restrict__ go, const float* __restric
                             BnBranch b2, int64_t n, int c) {
   const int64_t total = n * c;
   const double inv_n = 1.0 / (double)n;
-  // parameter gradients (train-mode BatchNorm): written once by the first CTA
+  // parameter gradients (train-mode BatchNorm): accumulated once, by the first CTA, into the caller's buffers
+  // (the parameters' .grad, or zero-filled temporaries)
   if (blockIdx.x == 0) {
     for (int ch = threadIdx.x; ch < c; ch += 256) {
       if (b1.red && b1.grad_gamma) {
-        b1.grad_gamma[ch] = (float)b1.red[c + ch];
-        b1.grad_beta[ch] = (float)b1.red[ch];
+        b1.grad_gamma[ch] += (float)b1.red[c + ch];
+        b1.grad_beta[ch] += (float)b1.red[ch];
       }
       if (b2.y && b2.red && b2.grad_gamma) {
-        b2.grad_gamma[ch] = (float)b2.red[c + ch];
-        b2.grad_beta[ch] = (float)b2.red[ch];
+        b2.grad_gamma[ch] += (float)b2.red[c + ch];
+        b2.grad_beta[ch] += (float)b2.red[ch];
       }
     }
   }

@@ -57,6 +57,49 @@ def _direct_grad(p: Optional[Tensor]) -> Optional[Tensor]:
     return g
 
 
+class _ScratchArena:
+    """Zero-filled scratch for the small reduction buffers of the backward pass (BatchNorm sums, encoder gradients, loss
+    accumulators): slices of one buffer that ``reset()`` clears with ONE memset at the start of the next forward instead
+    of one fill kernel per buffer (~90 launches per training step).  A slice may only be handed to consumers that finish
+    within the same forward/backward pass; when the arena is full callers fall back to ``torch.zeros``."""
+
+    def __init__(self, device: torch.device, nbytes: int = 1 << 20):
+        self.buf = torch.zeros(nbytes, dtype=torch.uint8, device=device)
+        self.off = 0
+
+    def take(self, numel: int, dtype: torch.dtype) -> Optional[Tensor]:
+        nbytes = (numel * torch.empty((), dtype=dtype).element_size() + 15) // 16 * 16
+        if self.off + nbytes > self.buf.numel():
+            return None
+        t = self.buf[self.off:self.off + nbytes].view(dtype)[:numel]
+        self.off += nbytes
+        return t
+
+    def reset(self) -> None:
+        if self.off:
+            self.buf[:self.off].zero_()
+        self.off = 0
+
+
+_ARENAS: dict = {}
+
+
+def reset_scratch(device: torch.device) -> None:
+    """Called by ``B200RandLANet.forward``: everything handed out since the last call is dead by now."""
+    a = _ARENAS.get(device.index if device.index is not None else torch.cuda.current_device())
+    if a is not None:
+        a.reset()
+
+
+def _zeros_scratch(numel: int, dtype: torch.dtype, device: torch.device) -> Tensor:
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    a = _ARENAS.get(key)
+    if a is None:
+        a = _ARENAS[key] = _ScratchArena(device)
+    t = a.take(numel, dtype)
+    return t if t is not None else torch.zeros(numel, dtype=dtype, device=device)
+
+
 def _need_cuda(*ts: Optional[Tensor]) -> None:
     for t in ts:
         if t is not None and not t.is_cuda:
@@ -140,6 +183,7 @@ class _EncoderFold(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, w, b, gamma, beta, moments, rm, rv, nbt, momentum, eps):
+        params = (w, b, gamma, beta)
         w, gamma, beta = _f32c(w), _f32c(gamma), _f32c(beta)
         b = _f32c(b) if b is not None else None
         h = w.shape[0]
@@ -151,6 +195,7 @@ class _EncoderFold(torch.autograd.Function):
         # eval-mode backward reads the (then unchanging) running statistics; train mode reads the moments
         ctx.save_for_backward(w, b, gamma, moments, None if training else rm, None if training else rv)
         ctx.eps = eps
+        ctx.params = params
         return enc_w, enc_b
 
     @staticmethod
@@ -158,12 +203,18 @@ class _EncoderFold(torch.autograd.Function):
     def backward(ctx, g_enc_w, g_enc_b):
         w, b, gamma, moments, rm, rv = ctx.saved_tensors
         h = w.shape[0]
+        direct = [_direct_grad(p) for p in ctx.params]
+        if all(d is not None or p is None for d, p in zip(direct, ctx.params)):  # accumulate into the .grad buffers
+            gw, gb, gg, gbeta = direct
+            _call("b200_encoder_fold_bwd", _p(w), _p(b), _p(gamma), _p(moments), _p(rm), _p(rv), ctx.eps,
+                  _p(_f32c(g_enc_w)), _p(_f32c(g_enc_b)), _p(gw), _p(gb), _p(gg), _p(gbeta), h, 1, _stream())
+            return (None,) * 10
         gw = torch.empty_like(w)
         gb = torch.empty_like(b) if b is not None else None
         gg = torch.empty_like(gamma)
         gbeta = torch.empty_like(gamma)
         _call("b200_encoder_fold_bwd", _p(w), _p(b), _p(gamma), _p(moments), _p(rm), _p(rv), ctx.eps,
-              _p(_f32c(g_enc_w)), _p(_f32c(g_enc_b)), _p(gw), _p(gb), _p(gg), _p(gbeta), h, _stream())
+              _p(_f32c(g_enc_w)), _p(_f32c(g_enc_b)), _p(gw), _p(gb), _p(gg), _p(gbeta), h, 0, _stream())
         return gw, gb, gg, gbeta, None, None, None, None, None, None
 
 
@@ -203,8 +254,9 @@ class _LFAFunction(torch.autograd.Function):
         n, h = x.shape
         c = 2 * h
         gx = torch.zeros_like(x)
-        gew = torch.zeros_like(enc_w)
-        geb = torch.zeros_like(enc_b)
+        small = _zeros_scratch(enc_w.numel() + enc_b.numel(), torch.float32, x.device)  # consumed by _EncoderFold.backward
+        gew = small[:enc_w.numel()].view_as(enc_w)
+        geb = small[enc_w.numel():]
         direct = _direct_grad(ctx.att_param)
         gaw = direct if direct is not None else torch.zeros_like(att_w)
         nbytes = int(_lib.load().b200_lfa_bwd_workspace_bytes(n, c, nbr.shape[1]))
@@ -295,6 +347,7 @@ class _Linear(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, a1, a2, w, b, want_stats):
+        ctx.set_materialize_grads(False)  # no zero-filled fp64 "gradient" for the statistics output
         w_param, b_param = w, b
         a1, w = _f32c(a1), _f32c(w)
         a2 = _f32c(a2) if a2 is not None else None
@@ -320,6 +373,8 @@ class _Linear(torch.autograd.Function):
     @staticmethod
     @once_differentiable
     def backward(ctx, grad_y, _grad_stats):
+        if grad_y is None:
+            return None, None, None, None, None
         a1, a2, w = ctx.saved_tensors
         grad_y = _f32c(grad_y)
         n, c1 = a1.shape
@@ -375,6 +430,7 @@ class _BNAct(torch.autograd.Function):
                                       _p(buf[0]), _p(buf[1]), _p(buf[2]), _p(buf[3]), c, _stream())
             return buf
 
+        params = (g1, b1, g2, b2)
         g1, b1 = _f32c(g1), _f32c(b1)
         y1 = _f32c(y1)
         aff1 = finalize(stats1, g1, b1, rm1, rv1, nbt1)
@@ -389,6 +445,7 @@ class _BNAct(torch.autograd.Function):
                                      _p(aff2[1]) if aff2 is not None else None, slope, _p(out), n, c, _stream())
         ctx.save_for_backward(y1, g1, aff1, y2, g2 if y2 is not None else None, aff2, out)
         ctx.slope, ctx.training = slope, training
+        ctx.params = params
         return out
 
     @staticmethod
@@ -399,24 +456,37 @@ class _BNAct(torch.autograd.Function):
         lib = _lib.load()
         n, c = y1.shape
         dev = y1.device
-        red1 = torch.zeros(2 * c, dtype=torch.float64, device=dev)
-        red2 = torch.zeros(2 * c, dtype=torch.float64, device=dev) if y2 is not None else None
+        red = _zeros_scratch(4 * c if y2 is not None else 2 * c, torch.float64, dev)  # consumed inside this call
+        red1 = red[:2 * c]
+        red2 = red[2 * c:] if y2 is not None else None
         _call("b200_affine_act_bwd_reduce", _p(grad_out), _p(out), ctx.slope, _p(y1), _p(aff1[2]), _p(aff1[3]), _p(red1),
                                             _p(y2), _p(aff2[2]) if y2 is not None else None,
                                             _p(aff2[3]) if y2 is not None else None, _p(red2), n, c, _stream())
         gy1 = torch.empty_like(y1)
         gy2 = torch.empty_like(y2) if y2 is not None else None
         tr = ctx.training
-        _call("b200_affine_act_bwd_apply", 
+        gg1 = gb1 = gg2 = gb2 = None
+        pg1 = pb1 = pg2 = pb2 = None  # where the kernel accumulates the BatchNorm affine gradients (train mode)
+        if tr:
+            pg1, pb1 = _direct_grad(ctx.params[0]), _direct_grad(ctx.params[1])
+            if pg1 is None or pb1 is None:  # no usable .grad buffer: zero-filled temporaries handed back to autograd
+                tmp = torch.zeros(2 * c, dtype=torch.float32, device=dev)  # (autograd may keep them as .grad: no arena)
+                pg1, pb1 = gg1, gb1 = tmp[:c], tmp[c:]
+            if y2 is not None:
+                pg2, pb2 = _direct_grad(ctx.params[2]), _direct_grad(ctx.params[3])
+                if pg2 is None or pb2 is None:
+                    tmp = torch.zeros(2 * c, dtype=torch.float32, device=dev)
+                    pg2, pb2 = gg2, gb2 = tmp[:c], tmp[c:]
+        _call("b200_affine_act_bwd_apply",
             _p(grad_out), _p(out), ctx.slope,
-            _p(y1), _p(g1), _p(aff1[2]), _p(aff1[3]), _p(red1) if tr else None, _p(aff1[0]), _p(gy1), None, None,
+            _p(y1), _p(g1), _p(aff1[2]), _p(aff1[3]), _p(red1) if tr else None, _p(aff1[0]), _p(gy1), _p(pg1), _p(pb1),
             _p(y2), _p(g2), _p(aff2[2]) if y2 is not None else None, _p(aff2[3]) if y2 is not None else None,
-            _p(red2) if (tr and y2 is not None) else None, _p(aff2[0]) if y2 is not None else None, _p(gy2), None, None,
+            _p(red2) if (tr and y2 is not None) else None, _p(aff2[0]) if y2 is not None else None, _p(gy2), _p(pg2), _p(pb2),
             n, c, _stream())
-        gg1, gb1 = red1[c:].float(), red1[:c].float()
-        gg2 = gb2 = None
-        if y2 is not None:
-            gg2, gb2 = red2[c:].float(), red2[:c].float()
+        if not tr:  # eval-mode statistics: the same sums are the affine gradients
+            gg1, gb1 = red1[c:].float(), red1[:c].float()
+            if y2 is not None:
+                gg2, gb2 = red2[c:].float(), red2[:c].float()
         return (gy1, None, gg1, gb1, None, None, None, gy2, None, gg2, gb2, None, None, None, None, None, None)
 
 
@@ -441,6 +511,50 @@ def bn_act(y: Tensor, stats: Optional[Tensor], bn: torch.nn.BatchNorm1d, slope: 
         args2 = (y2, stats2, bn2.weight, bn2.bias, rm2, rv2, bn2.num_batches_tracked)
     return _BNAct.apply(y, stats, bn.weight, bn.bias, rm1, rv1, bn.num_batches_tracked, *args2, float(slope),
                         float(bn.momentum), float(bn.eps))
+
+
+# ------------------------------------------------------------------------------ loss
+class _CrossEntropy(torch.autograd.Function):
+    """``torch.nn.CrossEntropyLoss(weight, ignore_index, reduction="mean")`` (models/model.py:117-118)."""
+
+    @staticmethod
+    def forward(ctx, logits, target, weight, ignore_index):
+        logits = _f32c(logits)
+        target = target.contiguous()
+        weight = _f32c(weight) if weight is not None else None
+        n, c = logits.shape
+        scratch = _zeros_scratch(4, torch.float64, logits.device)  # [sum, weight sum] fp64 + a uint32 CTA counter
+        out = torch.empty(2, dtype=torch.float32, device=logits.device)
+        _call("b200_cross_entropy_fwd", _p(logits), _p(target), _p(weight), n, c, int(ignore_index), _p(scratch[:2]),
+              _p(scratch[2:]), _p(out), _stream())
+        ctx.save_for_backward(logits, target, weight, out)
+        ctx.ignore_index = int(ignore_index)
+        return out[0]
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_loss):
+        logits, target, weight, out = ctx.saved_tensors
+        n, c = logits.shape
+        grad = torch.empty_like(logits)
+        g = _f32c(grad_loss).reshape(1)
+        _call("b200_cross_entropy_bwd", _p(logits), _p(target), _p(weight), n, c, ctx.ignore_index, _p(out), _p(g),
+              _p(grad), _stream())
+        return grad, None, None, None
+
+
+CROSS_ENTROPY_MAX_CLASSES = 32
+
+
+def cross_entropy(logits: Tensor, target: Tensor, weight: Optional[Tensor] = None, ignore_index: int = -100) -> Tensor:
+    """Mean cross-entropy over the rows whose target is not ``ignore_index`` (class-weighted mean if ``weight``)."""
+    _need_cuda(logits, target, weight)
+    if logits.dim() != 2 or target.shape != logits.shape[:1] or target.dtype != torch.int64:
+        raise ValueError(f"cross_entropy expects [N, C] logits and int64 [N] targets, got {tuple(logits.shape)}, "
+                         f"{tuple(target.shape)} {target.dtype}")
+    if weight is not None and weight.shape != (logits.shape[1],):
+        raise ValueError("weight must have one entry per class")
+    return _CrossEntropy.apply(logits, target, weight, ignore_index)
 
 
 # ------------------------------------------------------------------------------ sliding-window stitch (SURVEY 8f-2)

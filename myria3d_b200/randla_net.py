@@ -118,14 +118,19 @@ class _Level:
         return sum(n * min(k, n) for n in self.sizes)
 
     def decimation_tables(self, new_ptr_host: Sequence[int]):
-        """(cloud id << 32 per point, positions kept per cloud) for :func:`fused_decimation_indices`."""
+        """(cloud id in the high key bits per point, positions kept per cloud, random bits per key) for
+        :func:`fused_decimation_indices`."""
         if self._decim_cache is None:
             dev = self.ptr.device
             sizes = torch.tensor(self.sizes, dtype=torch.int64)
             cloud = torch.repeat_interleave(torch.arange(len(self.sizes), dtype=torch.int64), sizes)
             take = torch.cat([torch.arange(self.ptr_host[b], self.ptr_host[b] + (new_ptr_host[b + 1] - new_ptr_host[b]),
                                            dtype=torch.int64) for b in range(len(self.sizes))])
-            self._decim_cache = ((cloud << 32).to(dev), take.to(dev))
+            bits = max(1, (len(self.sizes) - 1).bit_length())
+            if bits <= 5:  # <= 32 clouds: (cloud id, >= 26 random bits) fits a non-negative int32 -> half the radix passes
+                self._decim_cache = ((cloud << (31 - bits)).to(torch.int32).to(dev), take.to(dev), 31 - bits)
+            else:
+                self._decim_cache = ((cloud << 32).to(dev), take.to(dev), 31)
         return self._decim_cache
 
 
@@ -218,8 +223,9 @@ def fused_decimation_indices(level: "_Level", new_ptr_host: Sequence[int]) -> Te
     (cloud id, key), one gather of each cloud's leading positions.  ~4 launches per level instead of
     ~7 per cloud (the reference's Python loop); the random stream differs from the
     reference's per-cloud ``randperm`` calls, the statistics do not."""
-    shift, take = level.decimation_tables(new_ptr_host)
-    keys = torch.randint(0, 2 ** 31 - 1, (level.n,), dtype=torch.int64, device=shift.device)
+    shift, take, random_bits = level.decimation_tables(new_ptr_host)
+    # ties between two keys of one cloud (expected < 1 pair per 12 800-point cloud at 27 bits) fall back to index order
+    keys = torch.randint(0, 2 ** random_bits - 1, (level.n,), dtype=shift.dtype, device=shift.device)
     order = torch.argsort(keys + shift)
     return order[take]
 
@@ -313,6 +319,7 @@ class B200RandLANet(nn.Module):
             raise RuntimeError("B200RandLANet runs on a CUDA (B200) device only; there is no CPU fallback")
         x = x if x is not None else pos  # :56
         pos = pos.float().contiguous()
+        ops.reset_scratch(pos.device)  # one memset for all the small zero-initialised buffers of the last pass
         if self.decimation < 1:
             decimation_sizes([0, 1], self.decimation)  # raises the reference's ValueError
         if self.static_ptr_host is not None:

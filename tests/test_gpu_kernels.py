@@ -448,3 +448,46 @@ def test_tcgen05_gemm_selftest(lib, n, k):
         assert int(status) == 0, "tcgen05 completion barrier timed out"
         err = float((d.double().cpu() - ref).abs().max())
         assert err <= tol * scale, f"passes={passes}: max err {err:.3e} vs scale {scale:.3e}"
+
+
+# ------------------------------------------------------------------------------ loss
+@pytest.mark.parametrize("n,c,weighted", [(5000, 6, False), (5000, 7, True), (3, 2, False), (70000, 32, True), (1, 6, False)])
+def test_cross_entropy_matches_torch(lib, n, c, weighted):
+    """ops.cross_entropy == torch.nn.CrossEntropyLoss(weight, ignore_index=65) (configs/model/criterion/*.yaml) in value
+    and gradient, with ignored rows (artefacts are mapped to 65, models/model.py:117-118)."""
+    import torch.nn.functional as F
+
+    from myria3d_b200 import ops
+
+    g = torch.Generator().manual_seed(n + c)
+    logits = (torch.randn(n, c, generator=g) * 3).to(DEV).requires_grad_(True)
+    target = torch.randint(0, c, (n,), generator=g)
+    if n > 2:
+        target[torch.rand(n, generator=g) < 0.2] = 65
+    target = target.to(DEV)
+    weight = (torch.rand(c, generator=g) + 0.5).to(DEV) if weighted else None
+    ref_in = logits.detach().double().requires_grad_(True)
+    ref = F.cross_entropy(ref_in, target, weight=weight.double() if weighted else None, ignore_index=65)
+    (ref * 1.7).backward()
+    loss = ops.cross_entropy(logits, target, weight, ignore_index=65)
+    (loss * 1.7).backward()
+    assert abs(float(loss) - float(ref)) <= 2e-6 * max(1.0, abs(float(ref)))
+    assert_close(logits.grad, ref_in.grad, atol=1e-7 + 2e-6 * float(ref_in.grad.abs().max()), what="dCE/dlogits")
+    assert not logits.grad[target == 65].any()
+
+
+def test_cross_entropy_all_ignored_is_nan_and_model_uses_it(lib):
+    from myria3d_b200 import ops
+    from myria3d_b200.model import Model
+
+    logits = torch.randn(10, 6, device=DEV)
+    target = torch.full((10,), 65, device=DEV)
+    assert torch.isnan(ops.cross_entropy(logits, target, None, 65))  # torch: 0 / 0
+    m = Model(neural_net_class_name="B200RandLANet",
+              neural_net_hparams=dict(num_features=9, num_classes=6, num_neighbors=16, decimation=4, return_logits=True),
+              criterion=torch.nn.CrossEntropyLoss(ignore_index=65), lr=1e-3)
+    t = torch.randint(0, 6, (10,), device=DEV)
+    want = torch.nn.functional.cross_entropy(logits, t, ignore_index=65)
+    assert abs(float(m._loss(logits, t)) - float(want)) < 1e-6
+    m.criterion = torch.nn.CrossEntropyLoss(ignore_index=65, label_smoothing=0.1)  # not the fused form: called as given
+    assert abs(float(m._loss(logits, t)) - float(m.criterion(logits, t))) == 0.0

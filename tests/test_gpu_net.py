@@ -238,3 +238,29 @@ def test_against_committed_golden_vectors(lib):
     bufs = dict(net.named_buffers())
     for k, v in g["buffers_after_step"].items():
         assert_close(bufs[k], v, atol=1e-5, rtol=1e-4, what=k)
+
+
+def test_param_grads_accumulate_into_existing_buffers(lib):
+    """Second backward on the same batch: every parameter already owns a dense .grad, so the kernels accumulate straight
+    into it (ops._direct_grad: Linear, BatchNorm affine, encoder fold, attention weights) -- the result must be exactly
+    twice... up to fp32 rounding of g + g == 2g, i.e. exactly 2x the first gradient wherever the first pass is
+    deterministic, and within 1e-5 relative where atomics reorder sums."""
+    ref, net = _pair(seed=21)
+    x, pos, batch, ptr = rand_cloud([900, 400], seed=21)
+    y = torch.randint(0, 6, (1300,), generator=torch.Generator().manual_seed(1)).to(DEV)
+    net.train()
+    net.mlp_classif.injected_masks = [None, (torch.rand(1300, 32, device=DEV) < 0.5).float() * 2.0]  # same dropout twice
+    args = (x.to(DEV), pos.to(DEV), batch.to(DEV), ptr.to(DEV))
+    out = net(*args)
+    idx = [t.clone() for t in net.last_decimation_idx]
+    F.cross_entropy(out, y).backward()
+    first = {n_: p.grad.clone() for n_, p in net.named_parameters()}
+    assert all(p.grad is not None for p in net.parameters())
+    net.injected_decimation_idx = idx
+    out = net(*args)  # batch statistics are identical; only the running buffers moved
+    F.cross_entropy(out, y).backward()
+    top = max(float(g.abs().max()) for g in first.values())
+    for n_, p in net.named_parameters():
+        scale = float(first[n_].abs().max())
+        # (biases in front of a BatchNorm have a mathematically zero gradient: fp32 noise, different on every run)
+        assert_close(p.grad, 2 * first[n_], atol=2e-5 * scale + 1e-6 * top, what=f"accumulated grad of {n_}")
