@@ -322,7 +322,10 @@ def run_b200(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+
+        # a collective that cannot complete (one rank died) aborts after 3 minutes instead of NCCL's default 10
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
 
     from myria3d_b200 import Model, _lib
     from myria3d_b200.build import build_library
@@ -434,12 +437,15 @@ def run_b200(args):
 
     # ---- per-kernel pass (CUDA events around every library call) for the roofline object
     table = []
-    if rank == 0 and args.profile_steps > 0:
-        prof = _lib.KernelProfiler()
+    if args.profile_steps > 0:
+        # every rank runs the eager steps (they contain the gradient all-reduce); rank 0 records the launches
+        prof = _lib.KernelProfiler() if rank == 0 else None
         _lib.PROFILER = prof
         for s in range(args.profile_steps):
             eager_step(resident[s % n_rot])  # eager: CUDA events around every library call
         _lib.PROFILER = None
+        torch.cuda.synchronize()
+    if rank == 0 and args.profile_steps > 0:
         recs = prof.summary()
         table = kernel_table([(n, i, ms / 1.0) for n, i, ms in recs])
         for g in table:

@@ -100,8 +100,11 @@ class GraphedTrainStep:
             torch.cuda.synchronize()
 
             n0 = _lib.launch_count()
+            # with a process group alive, NCCL's watchdog thread may touch the CUDA API while we capture: only calls of
+            # THIS thread may invalidate the capture then
+            mode = "thread_local" if multi else "global"
             cap.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(cap.graph):
+            with torch.cuda.graph(cap.graph, capture_error_mode=mode):
                 out = self._fwd_bwd(cap)
                 if not multi:
                     self.optimizer.step()
@@ -110,7 +113,7 @@ class GraphedTrainStep:
             cap.launches_per_step = _lib.launch_count() - n0
             if multi:
                 cap.opt_graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(cap.opt_graph):
+                with torch.cuda.graph(cap.opt_graph, capture_error_mode=mode):
                     self.optimizer.step()
         finally:
             self.net.static_ptr_host, self.net.injected_decimation_idx = prev_static, prev_inj
