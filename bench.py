@@ -150,7 +150,7 @@ def algorithmic_bytes(name: str, a):
         _ld1, c1, _ld2, c2, n, cout = a
         return 4 * n * (c1 + c2 + cout)
     if name == "b200_linear_bwd_input":
-        _l1, c1, _l2, c2, n, cout = a
+        _l1, c1, _l2, c2, _ws, n, cout = a
         return 4 * n * (c1 + c2 + cout)
     if name == "b200_linear_bwd_weight":
         _l1, c1, _l2, c2, _ws, n, cout = a
@@ -185,8 +185,11 @@ def algorithmic_flops(name: str, a):
     if name == "b200_lfa_bwd":
         _ws, n, c, kt = a
         return n * kt * (20 * c + 6 * c * c)
-    if name in ("b200_linear_fwd", "b200_linear_bwd_input"):
+    if name == "b200_linear_fwd":
         _l1, c1, _l2, c2, n, cout = a
+        return 2 * n * (c1 + c2) * cout
+    if name == "b200_linear_bwd_input":
+        _l1, c1, _l2, c2, _ws, n, cout = a
         return 2 * n * (c1 + c2) * cout
     if name == "b200_linear_bwd_weight":
         _l1, c1, _l2, c2, _ws, n, cout = a

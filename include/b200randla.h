@@ -177,9 +177,15 @@ int64_t b200_linear_fwd_num_stat_partials(int64_t n, int32_t c1, int32_t c2, int
 int b200_linear_fwd(const float* a1, int64_t ld1, int32_t c1, const float* a2, int64_t ld2, int32_t c2,
                     const float* w, const float* bias, float* y, int64_t n, int32_t cout,
                     double* colstats, void* stream);
-/* grad_a[n, c1+c2 split as ga1|ga2] = grad_y W ; either output may be NULL (skipped). */
+/* grad_a[n, c1+c2 split as ga1|ga2] = grad_y W ; either output may be NULL (skipped).
+ * workspace (16-byte aligned, b200_linear_bwd_input_workspace_bytes(), may be NULL / 0): holds W^T for the
+ * tensor-core path (layers with >= 64 input and output channels); without it the fp32-FMA kernel runs.
+ * Layers with >= 64 input and output channels (and c1 % 32 == 0) run on tcgen05 (3xTF32) in b200_linear_fwd /
+ * b200_linear_bwd_input and then require 16-byte aligned rows. */
+int64_t b200_linear_bwd_input_workspace_bytes(int64_t n, int32_t c1, int32_t c2, int32_t cout);
 int b200_linear_bwd_input(const float* grad_y, const float* w, float* ga1, int64_t ldg1, int32_t c1,
-                          float* ga2, int64_t ldg2, int32_t c2, int64_t n, int32_t cout, void* stream);
+                          float* ga2, int64_t ldg2, int32_t c2, void* workspace, int64_t workspace_bytes,
+                          int64_t n, int32_t cout, void* stream);
 /* grad_w[cout, c1+c2] += grad_y^T [a1|a2];  grad_bias[cout] += column sums of grad_y
  * (both ACCUMULATED: caller zero-fills; grad_bias may be NULL).  >= 64 x 64 weights run on the tensor cores
  * (tcgen05, 3xTF32 split: fp32-grade accuracy).  `workspace` (optional; 16-byte aligned,

@@ -36,7 +36,8 @@ _SIGNATURES = {
     "b200_knn_interp_fwd": (c_int, [_P, _P, _P, _P, c_int64, c_int32, c_int32, c_int32, c_int64, _P]),
     "b200_knn_interp_bwd": (c_int, [_P, c_int64, _P, _P, _P, c_int64, c_int32, c_int32, c_int32, _P]),
     "b200_linear_fwd": (c_int, [_P, c_int64, c_int32, _P, c_int64, c_int32, _P, _P, _P, c_int64, c_int32, _P, _P]),
-    "b200_linear_bwd_input": (c_int, [_P, _P, _P, c_int64, c_int32, _P, c_int64, c_int32, c_int64, c_int32, _P]),
+    "b200_linear_bwd_input_workspace_bytes": (c_int64, [c_int64, c_int32, c_int32, c_int32]),
+    "b200_linear_bwd_input": (c_int, [_P, _P, _P, c_int64, c_int32, _P, c_int64, c_int32, _P, c_int64, c_int64, c_int32, _P]),
     "b200_linear_bwd_weight_workspace_bytes": (c_int64, [c_int64, c_int32, c_int32, c_int32, c_int32]),
     "b200_linear_bwd_weight": (c_int, [_P, _P, c_int64, c_int32, _P, c_int64, c_int32, _P, _P, _P, c_int64, c_int64, c_int32, _P]),
     "b200_linear_fwd_num_stat_partials": (c_int64, [c_int64, c_int32, c_int32, c_int32]),

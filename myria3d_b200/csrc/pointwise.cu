@@ -770,6 +770,8 @@ extern "C" int b200_linear_fwd(const float* a1, int64_t ld1, int32_t c1, const f
   B200_REQUIRE(ld1 >= c1 && (c2 == 0 || ld2 >= c2), B200_E_INVALID, "b200_linear_fwd: row stride < width");
   if (n <= 0) return B200_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (tc_nt_shape_ok(n, c1, c2, cout))  // tcgen05 (3xTF32): every layer with >= 64 input and output channels
+    return launch_tc_nt(a1, ld1, c1, a2, ld2, c2, w, cout, bias, y, cout, cout, nullptr, 0, colstats, n, st);
   const CatRows A = make_cat(a1, ld1, c1, a2, ld2, c2);
   const bool wvec = aligned16(w) && ((c1 + c2) % 4 == 0);
   if (cout <= 32) {
@@ -786,13 +788,26 @@ extern "C" int b200_linear_fwd(const float* a1, int64_t ld1, int32_t c1, const f
   return B200_OK;
 }
 
+extern "C" int64_t b200_linear_bwd_input_workspace_bytes(int64_t n, int32_t c1, int32_t c2, int32_t cout) {
+  return tc_nt_shape_ok(n, cout, 0, c1 + c2) ? (int64_t)(c1 + c2) * cout * (int64_t)sizeof(float) : 0;
+}
+
 extern "C" int b200_linear_bwd_input(const float* grad_y, const float* w, float* ga1, int64_t ldg1, int32_t c1,
-                                     float* ga2, int64_t ldg2, int32_t c2, int64_t n, int32_t cout, void* stream) {
+                                     float* ga2, int64_t ldg2, int32_t c2, void* workspace, int64_t workspace_bytes,
+                                     int64_t n, int32_t cout, void* stream) {
   B200_REQUIRE(grad_y && w, B200_E_INVALID, "b200_linear_bwd_input: null pointer");
   B200_REQUIRE(c1 > 0 && c2 >= 0 && cout > 0, B200_E_INVALID, "b200_linear_bwd_input: bad sizes");
   if (n <= 0 || (!ga1 && !ga2)) return B200_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int ktot = c1 + c2;
+  if (workspace && workspace_bytes >= (int64_t)ktot * cout * (int64_t)sizeof(float) && aligned16(workspace) &&
+      tc_nt_shape_ok(n, cout, 0, ktot)) {
+    // tcgen05: grad_a[i][k] = sum_m grad_y[i][m] * W^T[k][m]; W^T goes to the workspace first (<= 1.5 MB)
+    float* wt = static_cast<float*>(workspace);
+    int rc = launch_transpose(w, wt, cout, ktot, st);
+    if (rc != B200_OK) return rc;
+    return launch_tc_nt(grad_y, cout, cout, nullptr, 0, 0, wt, ktot, nullptr, ga1, ldg1, c1, ga2, ldg2, nullptr, n, st);
+  }
   const bool gvec = aligned16(grad_y) && (cout % 4 == 0);
   const bool wvec = aligned16(w) && (ktot % 4 == 0);
   if (ktot <= 32) {
@@ -834,6 +849,7 @@ extern "C" int b200_linear_bwd_weight(const float* grad_y, const float* a1, int6
 
 extern "C" int64_t b200_linear_fwd_num_stat_partials(int64_t n, int32_t c1, int32_t c2, int32_t cout) {
   if (n <= 0) return 0;
+  if (tc_nt_shape_ok(n, c1, c2, cout)) return ceil_div(n, tc_nt_rows_per_tile(n, cout));
   if (cout <= 32) return ceil_div(n, 128);
   if (cout >= 128 && c1 + c2 >= 64 && ceil_div(n, 128) * ceil_div(cout, 128) >= num_sms()) return ceil_div(n, 128);
   return ceil_div(n, 64);

@@ -384,7 +384,10 @@ class _Linear(torch.autograd.Function):
         ga1 = torch.empty_like(a1) if ctx.needs_input_grad[0] else None
         ga2 = torch.empty_like(a2) if (a2 is not None and ctx.needs_input_grad[1]) else None
         if ga1 is not None or ga2 is not None:
-            _call("b200_linear_bwd_input", _p(grad_y), _p(w), _p(ga1), c1, c1, _p(ga2), c2, c2, n, cout, _stream())
+            nb = int(lib.b200_linear_bwd_input_workspace_bytes(n, c1, c2, cout))
+            wsi = torch.empty(nb, dtype=torch.uint8, device=w.device) if nb else None
+            _call("b200_linear_bwd_input", _p(grad_y), _p(w), _p(ga1), c1, c1, _p(ga2), c2, c2, _p(wsi), nb, n, cout,
+                  _stream())
         gw = gb = None
         if ctx.needs_input_grad[2] or (ctx.has_bias and ctx.needs_input_grad[3]):
             dw = _direct_grad(ctx.w_param)

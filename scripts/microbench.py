@@ -116,10 +116,11 @@ for l, c1, c2, cout in [(0, 9, 0, 32), (0, 32, 0, 32), (0, 32, 0, 4), (0, 16, 0,
     key = f"{c1}+{c2}->{cout}@L{l}"
     fl = 2 * nt * (c1 + c2) * cout
     by = 4 * nt * (c1 + c2 + cout)
+    wsi = torch.empty(max(int(lib.b200_linear_bwd_input_workspace_bytes(nt, c1, c2, cout)), 16), dtype=torch.uint8, device=dev)
     bench("linear_fwd", key, lambda a1=a1, a2=a2, w=w, bias=bias, y=y, stats=stats, nt=nt, c1=c1, c2=c2, cout=cout:
           _lib.check(lib.b200_linear_fwd(_p(a1), c1, c1, _p(a2), c2, c2, _p(w), _p(bias), _p(y), nt, cout, _p(stats), _stream()), "lf"), by, fl)
     bench("linear_bwd_input", key, lambda gy=gy, w=w, ga1=ga1, ga2=ga2, nt=nt, c1=c1, c2=c2, cout=cout:
-          _lib.check(lib.b200_linear_bwd_input(_p(gy), _p(w), _p(ga1), c1, c1, _p(ga2), c2, c2, nt, cout, _stream()), "lbi"), by, fl)
+          _lib.check(lib.b200_linear_bwd_input(_p(gy), _p(w), _p(ga1), c1, c1, _p(ga2), c2, c2, _p(wsi), wsi.numel(), nt, cout, _stream()), "lbi"), by, fl)
     wsb = int(lib.b200_linear_bwd_weight_workspace_bytes(nt, c1, c2, cout, 1))
     wsw = torch.empty(max(wsb, 16), dtype=torch.uint8, device=dev)
     bench("linear_bwd_weight", key, lambda gy=gy, a1=a1, a2=a2, gw=gw, gb=gb, nt=nt, c1=c1, c2=c2, cout=cout, wsw=wsw, wsb=wsb:

@@ -290,6 +290,39 @@ def test_linear_weight_grad_tensor_cores(lib, n, c1, c2, cout):
     assert rel_err(ag[2].grad, gb_ref) < 5e-6, rel_err(ag[2].grad, gb_ref)
 
 
+@pytest.mark.parametrize("n,c1,c2,cout", [(5000, 128, 0, 256), (4100, 256, 128, 128), (40000, 64, 0, 64), (3000, 512, 256, 256),
+                                          (1030, 64, 0, 70), (1024, 96, 32, 512), (2500, 64, 64, 100), (30000, 32, 0, 128)])
+def test_linear_tensor_core_forward_and_input_grad(lib, n, c1, c2, cout):
+    """Layers with >= 64 input and output channels run on tcgen05 (tc_nt.cu, 3xTF32, channels on TMEM lanes): output,
+    BatchNorm column statistics and input gradients against fp64 -- fp32-grade (rel 2e-6), ragged last row tile,
+    channel counts that are not multiples of 128, two-segment input/output."""
+    from myria3d_b200 import ops
+
+    g = torch.Generator().manual_seed(n + cout)
+    a1 = torch.randn(n, c1, generator=g)
+    a2 = torch.randn(n, c2, generator=g) if c2 else None
+    w = torch.randn(cout, c1 + c2, generator=g) / (c1 + c2) ** 0.5
+    b = torch.randn(cout, generator=g)
+    gy = torch.randn(n, cout, generator=g)
+    inp = (torch.cat([a1, a2], 1) if c2 else a1).double()
+    y_ref = inp @ w.double().t() + b.double()
+    ga_ref = gy.double() @ w.double()
+    ag = [t.to(DEV).requires_grad_(True) for t in (a1, w, b)] + ([a2.to(DEV).requires_grad_(True)] if c2 else [])
+    y, stats = ops.linear(ag[0], ag[1], ag[2], a2=ag[3] if c2 else None, want_stats=True)
+    y.backward(gy.to(DEV))
+    assert rel_err(y, y_ref) < 4e-6, rel_err(y, y_ref)  # fp32 accumulation over up to 768 terms
+    assert_close(y, y_ref, atol=2e-5, rtol=1e-5, what="linear y (tcgen05)")
+    stats = stats.sum(0)
+    assert_close(stats[:cout], y_ref.sum(0), atol=1e-3, rtol=1e-5, what="column sums")
+    assert_close(stats[cout:], (y_ref ** 2).sum(0), atol=1e-3, rtol=1e-5, what="column sums of squares")
+    assert rel_err(ag[0].grad, ga_ref[:, :c1]) < 4e-6, rel_err(ag[0].grad, ga_ref[:, :c1])
+    if c2:
+        assert rel_err(ag[3].grad, ga_ref[:, c1:]) < 4e-6, rel_err(ag[3].grad, ga_ref[:, c1:])
+    # and bit-for-bit insensitive to what lies beyond the last row (no stale shared memory / TMEM in the ragged tile)
+    y2 = ops.linear(ag[0].detach(), ag[1].detach(), ag[2].detach(), a2=ag[3].detach() if c2 else None)
+    assert torch.equal(y2, y.detach())
+
+
 @pytest.mark.parametrize("n,c1,c2,cout", [(1000, 9, 0, 32), (777, 32, 32, 32), (130, 512, 256, 256), (2048, 32, 0, 7),
                                           (65, 64, 0, 64), (3, 4, 0, 8), (515, 128, 32, 32)])
 def test_linear_fwd_bwd(lib, n, c1, c2, cout):
