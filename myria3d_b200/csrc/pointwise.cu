@@ -788,8 +788,12 @@ extern "C" int b200_linear_fwd(const float* a1, int64_t ld1, int32_t c1, const f
   return B200_OK;
 }
 
+// Input gradients go to the tensor cores below level 1 only: on >= 51 200 rows the layers are HBM-bound and the FMA
+// kernel (no transpose pass, no idle TMEM lanes for narrow outputs) is as fast or faster (profiles/).
+static bool bwd_input_uses_tc(int64_t n, int ktot, int cout) { return n <= 32768 && tc_nt_shape_ok(n, cout, 0, ktot); }
+
 extern "C" int64_t b200_linear_bwd_input_workspace_bytes(int64_t n, int32_t c1, int32_t c2, int32_t cout) {
-  return tc_nt_shape_ok(n, cout, 0, c1 + c2) ? (int64_t)(c1 + c2) * cout * (int64_t)sizeof(float) : 0;
+  return bwd_input_uses_tc(n, c1 + c2, cout) ? (int64_t)(c1 + c2) * cout * (int64_t)sizeof(float) : 0;
 }
 
 extern "C" int b200_linear_bwd_input(const float* grad_y, const float* w, float* ga1, int64_t ldg1, int32_t c1,
@@ -801,7 +805,7 @@ extern "C" int b200_linear_bwd_input(const float* grad_y, const float* w, float*
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int ktot = c1 + c2;
   if (workspace && workspace_bytes >= (int64_t)ktot * cout * (int64_t)sizeof(float) && aligned16(workspace) &&
-      tc_nt_shape_ok(n, cout, 0, ktot)) {
+      bwd_input_uses_tc(n, ktot, cout)) {
     // tcgen05: grad_a[i][k] = sum_m grad_y[i][m] * W^T[k][m]; W^T goes to the workspace first (<= 1.5 MB)
     float* wt = static_cast<float*>(workspace);
     int rc = launch_transpose(w, wt, cout, ktot, st);

@@ -37,7 +37,7 @@ struct NtOut {  // channel m < c1 -> o1[row * ld1 + m], else o2[row * ld2 + m - 
 template <int BN>
 __global__ void __launch_bounds__(TNT_THREADS, 1)
 tc_nt_kernel(NtRows X, const float* __restrict__ wm, int mrows, const float* __restrict__ bias, NtOut O,
-             double* __restrict__ colstats /* [row tiles][2 * mrows] or nullptr */, int64_t n) {
+             double* __restrict__ colstats /* [row tiles][2 * mrows] or nullptr */, int64_t n, int m_tiles, int total_tiles) {
   extern __shared__ __align__(128) float tnt_smem[];
   __shared__ __align__(8) uint64_t bars[2];
   __shared__ uint32_t tmem_slot;
@@ -49,8 +49,6 @@ tc_nt_kernel(NtRows X, const float* __restrict__ wm, int mrows, const float* __r
   constexpr int WQ = 128 * 8 / TNT_THREADS;
 
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int m0 = blockIdx.x * 128;
-  const int64_t i0 = (int64_t)blockIdx.y * BN;
   const int ktot = X.c1 + X.c2;
   const int nchunks = ktot / TNT_KC;
 
@@ -70,7 +68,9 @@ tc_nt_kernel(NtRows X, const float* __restrict__ wm, int mrows, const float* __r
   // item = tid + q * 256 -> operand row item / 8, 16-byte k-group item % 8 (8 lanes read one row's 128 bytes;
   // their STS.128 hit 8 different bank groups because the k-group pitch (rows + 1) * 16 B is odd in 16-byte units)
   float4 xr[XQ], wr[WQ];
-  auto load_chunk = [&](int k0) {
+  auto load_chunk = [&](int tile, int k0) {  // tile -> (row tile, channel tile): neighbouring CTAs share the rows in L2
+    const int m0 = (tile % m_tiles) * 128;
+    const int64_t i0 = (int64_t)(tile / m_tiles) * BN;
 #pragma unroll
     for (int q = 0; q < XQ; ++q) {
       const int item = tid + q * TNT_THREADS, r = item >> 3, k = k0 + 4 * (item & 7);
@@ -101,96 +101,111 @@ tc_nt_kernel(NtRows X, const float* __restrict__ wm, int mrows, const float* __r
     *reinterpret_cast<float4*>(lo_base + off) = lo;
   };
 
-  load_chunk(0);
-  for (int s = 0; s < nchunks && alive; ++s) {
-    const int stage = s & 1;
-    float* Wh = tnt_smem + stage * STAGE_FLOATS;
-    float* Wl = Wh + W_FLOATS;
-    float* Xh = Wl + W_FLOATS;
-    float* Xl = Xh + X_FLOATS;
-    // the stage may be overwritten only after the MMAs of chunk s-2 (its previous user) have completed
-    if (s >= 2) {
-      alive = tc::mbar_wait_bounded(&bars[stage], (uint32_t)(((s - 2) >> 1) & 1));
-      alive = __syncthreads_and(alive) != 0;
-    }
-    if (!alive) break;
+  // Persistent CTA: tiles blockIdx.x, + gridDim.x, ...  `g` counts the K-chunks this CTA has issued over all its tiles:
+  // chunk g uses stage g & 1, whose mbarrier completes its (g >> 1)-th phase when the chunk's MMAs are done.  The
+  // first chunk of the NEXT tile is fetched into registers before the epilogue of the current one, so its DRAM
+  // latency hides behind the TMEM read-out and the output stores.
+  int g = 0;
+  if ((int)blockIdx.x < total_tiles) load_chunk(blockIdx.x, 0);
+  for (int tile = blockIdx.x; tile < total_tiles && alive; tile += gridDim.x) {
+    const int m0 = (tile % m_tiles) * 128;
+    const int64_t i0 = (int64_t)(tile / m_tiles) * BN;
+    for (int s = 0; s < nchunks && alive; ++s, ++g) {
+      const int stage = g & 1;
+      float* Wh = tnt_smem + stage * STAGE_FLOATS;
+      float* Wl = Wh + W_FLOATS;
+      float* Xh = Wl + W_FLOATS;
+      float* Xl = Xh + X_FLOATS;
+      // the stage may be overwritten only after the MMAs of chunk g-2 (its previous user) have completed
+      if (g >= 2) {
+        alive = tc::mbar_wait_bounded(&bars[stage], (uint32_t)(((g - 2) >> 1) & 1));
+        alive = __syncthreads_and(alive) != 0;
+      }
+      if (!alive) break;
 #pragma unroll
-    for (int q = 0; q < WQ; ++q) split_store(Wh, Wl, 129, tid + q * TNT_THREADS, wr[q]);
+      for (int q = 0; q < WQ; ++q) split_store(Wh, Wl, 129, tid + q * TNT_THREADS, wr[q]);
 #pragma unroll
-    for (int q = 0; q < XQ; ++q) split_store(Xh, Xl, BN + 1, tid + q * TNT_THREADS, xr[q]);
-    if (s + 1 < nchunks) load_chunk((s + 1) * TNT_KC);  // prefetch: consumed next iteration
+      for (int q = 0; q < XQ; ++q) split_store(Xh, Xl, BN + 1, tid + q * TNT_THREADS, xr[q]);
+      if (s + 1 < nchunks)
+        load_chunk(tile, (s + 1) * TNT_KC);  // prefetch: consumed next iteration
+      else if (tile + (int)gridDim.x < total_tiles)
+        load_chunk(tile + gridDim.x, 0);     // ... or by the next tile, after this tile's epilogue
 
-    tc::fence_smem_to_async();
-    tc::fence_before_sync();
-    __syncthreads();
+      tc::fence_smem_to_async();
+      tc::fence_before_sync();
+      __syncthreads();
+      tc::fence_after_sync();
+      if (tid == 0) {
+        const uint32_t lbo_w = tc::lbo_bytes(128), lbo_x = tc::lbo_bytes(BN);
+#pragma unroll
+        for (int pass = 0; pass < 3; ++pass) {
+          const uint32_t a_base = smem_u32((pass == 1) ? Wl : Wh);  // hi*hi, lo*hi, hi*lo
+          const uint32_t b_base = smem_u32((pass == 2) ? Xl : Xh);
+#pragma unroll
+          for (int ks = 0; ks < TNT_KC / 8; ++ks) {
+            const uint64_t ad = tc::smem_desc(a_base + (uint32_t)(2 * ks) * lbo_w, lbo_w, tc::kSboBytes);
+            const uint64_t bd = tc::smem_desc(b_base + (uint32_t)(2 * ks) * lbo_x, lbo_x, tc::kSboBytes);
+            tc::mma_tf32(tmem_d, ad, bd, idesc, (s | pass | ks) != 0);
+          }
+        }
+        tc::mma_commit(&bars[stage]);
+      }
+    }
+
+    if (alive) {
+      const int last = g - 1;
+      alive = tc::mbar_wait_bounded(&bars[last & 1], (uint32_t)((last >> 1) & 1));
+    }
+    alive = __syncthreads_and(alive) != 0;
     tc::fence_after_sync();
-    if (tid == 0) {
-      const uint32_t lbo_w = tc::lbo_bytes(128), lbo_x = tc::lbo_bytes(BN);
-#pragma unroll
-      for (int pass = 0; pass < 3; ++pass) {
-        const uint32_t a_base = smem_u32((pass == 1) ? Wl : Wh);  // hi*hi, lo*hi, hi*lo
-        const uint32_t b_base = smem_u32((pass == 2) ? Xl : Xh);
-#pragma unroll
-        for (int ks = 0; ks < TNT_KC / 8; ++ks) {
-          const uint64_t ad = tc::smem_desc(a_base + (uint32_t)(2 * ks) * lbo_w, lbo_w, tc::kSboBytes);
-          const uint64_t bd = tc::smem_desc(b_base + (uint32_t)(2 * ks) * lbo_x, lbo_x, tc::kSboBytes);
-          tc::mma_tf32(tmem_d, ad, bd, idesc, (s | pass | ks) != 0);
+    if (alive) {
+      // warp w reads TMEM lanes 32*(w%4) .. +31 (= channels) and the row half w/4
+      const int lane_q = warp & 3, half = warp >> 2;
+      const int ml = lane_q * 32 + (tid & 31);
+      const int m = m0 + ml;
+      const bool mok = m < mrows;
+      const float b = (bias && mok) ? __ldg(bias + m) : 0.f;
+      float* obase = nullptr;
+      int64_t old = 0;
+      if (mok) {
+        if (m < O.c1) {
+          if (O.o1) obase = O.o1 + m, old = O.ld1;
+        } else if (O.o2) {
+          obase = O.o2 + (m - O.c1), old = O.ld2;
         }
       }
-      tc::mma_commit(&bars[stage]);
-    }
-  }
-
-  if (alive) {
-    const int last = nchunks - 1;
-    alive = tc::mbar_wait_bounded(&bars[last & 1], (uint32_t)((last >> 1) & 1));
-  }
-  alive = __syncthreads_and(alive) != 0;
-  tc::fence_after_sync();
-  if (alive) {
-    // warp w reads TMEM lanes 32*(w%4) .. +31 (= channels) and the row half w/4
-    const int lane_q = warp & 3, half = warp >> 2;
-    const int ml = lane_q * 32 + (tid & 31);
-    const int m = m0 + ml;
-    const bool mok = m < mrows;
-    const float b = (bias && mok) ? __ldg(bias + m) : 0.f;
-    float* obase = nullptr;
-    int64_t old = 0;
-    if (mok) {
-      if (m < O.c1) {
-        if (O.o1) obase = O.o1 + m, old = O.ld1;
-      } else if (O.o2) {
-        obase = O.o2 + (m - O.c1), old = O.ld2;
-      }
-    }
-    double s1 = 0.0, s2 = 0.0;
+      double s1 = 0.0, s2 = 0.0;
 #pragma unroll 1
-    for (int cc = half * (BN / 2); cc < (half + 1) * (BN / 2); cc += 16) {
-      float v[16];
-      tc::tmem_ld16(tmem_d + ((uint32_t)(lane_q * 32) << 16) + (uint32_t)cc, v);
+      for (int cc = half * (BN / 2); cc < (half + 1) * (BN / 2); cc += 16) {
+        float v[16];
+        tc::tmem_ld16(tmem_d + ((uint32_t)(lane_q * 32) << 16) + (uint32_t)cc, v);
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int64_t row = i0 + cc + j;
-        if (row < n) {
-          const float y = v[j] + b;
-          if (obase) obase[row * old] = y;
-          s1 += (double)y;
-          s2 += (double)y * (double)y;
+        for (int j = 0; j < 16; ++j) {
+          const int64_t row = i0 + cc + j;
+          if (row < n) {
+            const float y = v[j] + b;
+            if (obase) obase[row * old] = y;
+            s1 += (double)y;
+            s2 += (double)y * (double)y;
+          }
         }
       }
+      if (colstats) {
+        stat_sh[half][ml][0] = s1;
+        stat_sh[half][ml][1] = s2;
+      }
     }
-    if (colstats) {
-      stat_sh[half][ml][0] = s1;
-      stat_sh[half][ml][1] = s2;
+    tc::fence_before_sync();
+    __syncthreads();  // TMEM drained (the next tile's first MMA overwrites it), stat_sh complete
+    tc::fence_after_sync();
+    if (alive && colstats && tid < 128 && m0 + tid < mrows) {
+      double* part = colstats + (int64_t)(tile / m_tiles) * 2 * mrows;
+      part[m0 + tid] = stat_sh[0][tid][0] + stat_sh[1][tid][0];
+      part[mrows + m0 + tid] = stat_sh[0][tid][1] + stat_sh[1][tid][1];
     }
   }
   tc::fence_before_sync();
   __syncthreads();
-  if (alive && colstats && tid < 128 && m0 + tid < mrows) {
-    double* part = colstats + (int64_t)blockIdx.y * 2 * mrows;
-    part[m0 + tid] = stat_sh[0][tid][0] + stat_sh[1][tid][0];
-    part[mrows + m0 + tid] = stat_sh[0][tid][1] + stat_sh[1][tid][1];
-  }
   if (warp == 0) tc::tmem_dealloc(tmem_d, BN);
 }
 
@@ -225,8 +240,11 @@ static int launch_tc_nt_bn(const NtRows& X, const float* wm, int mrows, const fl
   auto kern = tc_nt_kernel<BN>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return cuda_fail(e, "tc_nt smem attribute");
-  dim3 grid((unsigned)ceil_div(mrows, 128), (unsigned)ceil_div(n, BN));
-  kern<<<grid, TNT_THREADS, smem, st>>>(X, wm, mrows, bias, O, colstats, n);
+  const int m_tiles = (int)ceil_div(mrows, 128);
+  const int64_t total = (int64_t)m_tiles * ceil_div(n, BN);
+  B200_REQUIRE(total < (1ll << 30), B200_E_UNSUPPORTED, "tensor-core linear layer: too many tiles");
+  const int grid = (int)(total < num_sms() ? total : num_sms());  // persistent: one CTA per SM
+  kern<<<grid, TNT_THREADS, smem, st>>>(X, wm, mrows, bias, O, colstats, n, m_tiles, (int)total);
   B200_CHECK_LAUNCH("tc_nt_kernel");
   return B200_OK;
 }
