@@ -277,6 +277,7 @@ tc_reduce_partials_kernel(const float* __restrict__ partial, int splits, int cou
 
 static long long* g_tc_debug = nullptr;  // timeline buffer (128 x int64) for scripts/tc_timeline.py; never set in production
 void set_tc_debug_buffer(long long* p) { g_tc_debug = p; }
+long long* tc_debug_buffer() { return g_tc_debug; }
 
 struct TcTnPlan {
   int bn;

@@ -37,8 +37,13 @@ struct NtOut {  // channel m < c1 -> o1[row * ld1 + m], else o2[row * ld2 + m - 
 template <int BN>
 __global__ void __launch_bounds__(TNT_THREADS, 1)
 tc_nt_kernel(NtRows X, const float* __restrict__ wm, int mrows, const float* __restrict__ bias, NtOut O,
-             double* __restrict__ colstats /* [row tiles][2 * mrows] or nullptr */, int64_t n, int m_tiles, int total_tiles) {
+             double* __restrict__ colstats /* [row tiles][2 * mrows] or nullptr */, int64_t n, int m_tiles, int total_tiles,
+             long long* __restrict__ dbg /* clock64 timeline of CTA 0 (scripts/nt_timeline.py); nullptr in production */) {
   extern __shared__ __align__(128) float tnt_smem[];
+  const bool rec = dbg && blockIdx.x == 0 && threadIdx.x == 32;
+  int nrec = 0;
+#define B200_TS() do { if (rec && nrec < 120) dbg[nrec++] = clock64(); } while (0)
+  B200_TS();  // [0]
   __shared__ __align__(8) uint64_t bars[2];
   __shared__ uint32_t tmem_slot;
   __shared__ double stat_sh[2][128][2];
@@ -52,7 +57,7 @@ tc_nt_kernel(NtRows X, const float* __restrict__ wm, int mrows, const float* __r
   const int ktot = X.c1 + X.c2;
   const int nchunks = ktot / TNT_KC;
 
-  if (warp == 0) tc::tmem_alloc(&tmem_slot, BN);
+  if (warp == 0) tc::tmem_alloc(&tmem_slot, 2 * BN);  // two accumulator buffers
   if (tid == 0) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
@@ -101,15 +106,103 @@ tc_nt_kernel(NtRows X, const float* __restrict__ wm, int mrows, const float* __r
     *reinterpret_cast<float4*>(lo_base + off) = lo;
   };
 
-  // Persistent CTA: tiles blockIdx.x, + gridDim.x, ...  `g` counts the K-chunks this CTA has issued over all its tiles:
-  // chunk g uses stage g & 1, whose mbarrier completes its (g >> 1)-th phase when the chunk's MMAs are done.  The
-  // first chunk of the NEXT tile is fetched into registers before the epilogue of the current one, so its DRAM
-  // latency hides behind the TMEM read-out and the output stores.
-  int g = 0;
-  if ((int)blockIdx.x < total_tiles) load_chunk(blockIdx.x, 0);
-  for (int tile = blockIdx.x; tile < total_tiles && alive; tile += gridDim.x) {
+  // Epilogue of one tile out of TMEM buffer `buf`: thread = channel, TMEM columns = rows.  Two 16-column loads are kept
+  // in flight (the next block travels while the current one is processed); the BatchNorm sums of a 16-row block are
+  // taken in fp32 and accumulated across blocks in fp64.
+  auto epilogue = [&](int tile, int buf) {
     const int m0 = (tile % m_tiles) * 128;
     const int64_t i0 = (int64_t)(tile / m_tiles) * BN;
+    const int lane_q = warp & 3, half = warp >> 2;  // warp w reads TMEM lanes 32*(w%4) .. +31 and the row half w/4
+    const int ml = lane_q * 32 + (tid & 31);
+    const int m = m0 + ml;
+    const bool mok = m < mrows;
+    const float b = (bias && mok) ? __ldg(bias + m) : 0.f;
+    float* obase = nullptr;
+    int64_t old = 0;
+    if (mok) {
+      if (m < O.c1) {
+        if (O.o1) obase = O.o1 + m, old = O.ld1;
+      } else if (O.o2) {
+        obase = O.o2 + (m - O.c1), old = O.ld2;
+      }
+    }
+    double s1 = 0.0, s2 = 0.0;
+    const bool st = obase != nullptr;
+    float* const pbase = st ? obase : nullptr;
+    const bool want_stats = colstats != nullptr;
+    auto process = [&](const uint32_t (&r)[16], int64_t row0) {
+      // (pointer bumps and predicated stores: a nullable pointer indexed with a 64-bit product per element compiled to a
+      // divergent branch region + ~10 integer instructions per store and made the epilogue 4x longer than the MMAs)
+      float y[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) y[j] = __uint_as_float(r[j]) + b;
+      const int64_t left = n - row0;
+      const int lim = left >= 16 ? 16 : (left < 0 ? 0 : (int)left);
+      float* p = pbase + row0 * old;
+      if (lim == 16) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          if (st) *p = y[j];
+          p += old;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          if (st && j < lim) *p = y[j];
+          p += old;
+        }
+      }
+      if (want_stats) {
+        float sa = 0.f, sq = 0.f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float v = (j < lim) ? y[j] : 0.f;
+          sa += v;
+          sq = fmaf(v, v, sq);
+        }
+        s1 += (double)sa;
+        s2 += (double)sq;
+      }
+    };
+    const uint32_t tbase = tmem_d + ((uint32_t)(lane_q * 32) << 16) + (uint32_t)(buf * BN + half * (BN / 2));
+    const int64_t rbase = i0 + half * (BN / 2);
+    uint32_t ra[16], rb[16];
+    tc::tmem_ld16_async(tbase, ra);
+    tc::tmem_ld_wait(ra);
+#pragma unroll 1
+    for (int cc = 0; cc < BN / 2; cc += 32) {
+      tc::tmem_ld16_async(tbase + (uint32_t)(cc + 16), rb);
+      process(ra, rbase + cc);
+      tc::tmem_ld_wait(rb);
+      if (cc + 32 < BN / 2) tc::tmem_ld16_async(tbase + (uint32_t)(cc + 32), ra);
+      process(rb, rbase + cc + 16);
+      if (cc + 32 < BN / 2) tc::tmem_ld_wait(ra);
+    }
+    if (colstats) {
+      stat_sh[half][ml][0] = s1;
+      stat_sh[half][ml][1] = s2;
+    }
+    B200_TS();  // tile: epilogue done (this warp)
+    tc::fence_before_sync();
+    __syncthreads();  // this TMEM buffer is drained (a later tile's first MMA overwrites it), stat_sh complete
+    tc::fence_after_sync();
+    if (colstats && tid < 128 && m0 + tid < mrows) {
+      double* part = colstats + (int64_t)(tile / m_tiles) * 2 * mrows;
+      part[m0 + tid] = stat_sh[0][tid][0] + stat_sh[1][tid][0];
+      part[mrows + m0 + tid] = stat_sh[0][tid][1] + stat_sh[1][tid][1];
+    }
+  };
+
+  // Persistent CTA: tiles blockIdx.x, + gridDim.x, ...  `g` counts the K-chunks this CTA has issued over all its tiles:
+  // chunk g uses stage g & 1, whose mbarrier completes its (g >> 1)-th phase when the chunk's MMAs are done.
+  // Tile t accumulates into TMEM buffer t & 1; its epilogue runs AFTER the MMAs of tile t+1 have been issued into the
+  // other buffer, so the tensor pipe works while the previous tile is read out and stored, and the first chunk of the
+  // tile after that is already travelling from DRAM.
+  int g = 0, it = 0, prev_tile = -1;
+  B200_TS();  // [1] after alloc/init
+  if ((int)blockIdx.x < total_tiles) load_chunk(blockIdx.x, 0);
+  for (int tile = blockIdx.x; tile < total_tiles && alive; tile += gridDim.x, ++it) {
+    const uint32_t tmem_acc = tmem_d + (uint32_t)((it & 1) * BN);
     for (int s = 0; s < nchunks && alive; ++s, ++g) {
       const int stage = g & 1;
       float* Wh = tnt_smem + stage * STAGE_FLOATS;
@@ -122,6 +215,7 @@ tc_nt_kernel(NtRows X, const float* __restrict__ wm, int mrows, const float* __r
         alive = __syncthreads_and(alive) != 0;
       }
       if (!alive) break;
+      B200_TS();  // chunk: stage free
 #pragma unroll
       for (int q = 0; q < WQ; ++q) split_store(Wh, Wl, 129, tid + q * TNT_THREADS, wr[q]);
 #pragma unroll
@@ -129,12 +223,14 @@ tc_nt_kernel(NtRows X, const float* __restrict__ wm, int mrows, const float* __r
       if (s + 1 < nchunks)
         load_chunk(tile, (s + 1) * TNT_KC);  // prefetch: consumed next iteration
       else if (tile + (int)gridDim.x < total_tiles)
-        load_chunk(tile + gridDim.x, 0);     // ... or by the next tile, after this tile's epilogue
+        load_chunk(tile + gridDim.x, 0);     // ... or by the next tile
+      B200_TS();  // chunk: stored + next loads issued
 
       tc::fence_smem_to_async();
       tc::fence_before_sync();
       __syncthreads();
       tc::fence_after_sync();
+      B200_TS();  // chunk: after barrier
       if (tid == 0) {
         const uint32_t lbo_w = tc::lbo_bytes(128), lbo_x = tc::lbo_bytes(BN);
 #pragma unroll
@@ -145,69 +241,44 @@ tc_nt_kernel(NtRows X, const float* __restrict__ wm, int mrows, const float* __r
           for (int ks = 0; ks < TNT_KC / 8; ++ks) {
             const uint64_t ad = tc::smem_desc(a_base + (uint32_t)(2 * ks) * lbo_w, lbo_w, tc::kSboBytes);
             const uint64_t bd = tc::smem_desc(b_base + (uint32_t)(2 * ks) * lbo_x, lbo_x, tc::kSboBytes);
-            tc::mma_tf32(tmem_d, ad, bd, idesc, (s | pass | ks) != 0);
+            tc::mma_tf32(tmem_acc, ad, bd, idesc, (s | pass | ks) != 0);
           }
         }
         tc::mma_commit(&bars[stage]);
       }
     }
-
-    if (alive) {
-      const int last = g - 1;
-      alive = tc::mbar_wait_bounded(&bars[last & 1], (uint32_t)((last >> 1) & 1));
+    if (!alive) break;
+    // the previous tile: with >= 2 chunks per tile its last chunk (g - nchunks - 1) was already awaited by this tile's
+    // second chunk (stage reuse); with one chunk per tile nothing has been committed to its barrier since, so the
+    // parity wait below is unambiguous
+    if (prev_tile >= 0) {
+      if (nchunks == 1) {
+        const int last = g - 2;
+        alive = tc::mbar_wait_bounded(&bars[last & 1], (uint32_t)((last >> 1) & 1));
+        alive = __syncthreads_and(alive) != 0;
+        tc::fence_after_sync();
+      }
+      B200_TS();  // tile: previous tile's MMAs complete
+      if (alive) epilogue(prev_tile, (it - 1) & 1);
     }
+    prev_tile = tile;
+  }
+  if (alive && prev_tile >= 0) {  // the last tile of this CTA
+    const int last = g - 1;
+    alive = tc::mbar_wait_bounded(&bars[last & 1], (uint32_t)((last >> 1) & 1));
     alive = __syncthreads_and(alive) != 0;
     tc::fence_after_sync();
-    if (alive) {
-      // warp w reads TMEM lanes 32*(w%4) .. +31 (= channels) and the row half w/4
-      const int lane_q = warp & 3, half = warp >> 2;
-      const int ml = lane_q * 32 + (tid & 31);
-      const int m = m0 + ml;
-      const bool mok = m < mrows;
-      const float b = (bias && mok) ? __ldg(bias + m) : 0.f;
-      float* obase = nullptr;
-      int64_t old = 0;
-      if (mok) {
-        if (m < O.c1) {
-          if (O.o1) obase = O.o1 + m, old = O.ld1;
-        } else if (O.o2) {
-          obase = O.o2 + (m - O.c1), old = O.ld2;
-        }
-      }
-      double s1 = 0.0, s2 = 0.0;
-#pragma unroll 1
-      for (int cc = half * (BN / 2); cc < (half + 1) * (BN / 2); cc += 16) {
-        float v[16];
-        tc::tmem_ld16(tmem_d + ((uint32_t)(lane_q * 32) << 16) + (uint32_t)cc, v);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int64_t row = i0 + cc + j;
-          if (row < n) {
-            const float y = v[j] + b;
-            if (obase) obase[row * old] = y;
-            s1 += (double)y;
-            s2 += (double)y * (double)y;
-          }
-        }
-      }
-      if (colstats) {
-        stat_sh[half][ml][0] = s1;
-        stat_sh[half][ml][1] = s2;
-      }
-    }
-    tc::fence_before_sync();
-    __syncthreads();  // TMEM drained (the next tile's first MMA overwrites it), stat_sh complete
-    tc::fence_after_sync();
-    if (alive && colstats && tid < 128 && m0 + tid < mrows) {
-      double* part = colstats + (int64_t)(tile / m_tiles) * 2 * mrows;
-      part[m0 + tid] = stat_sh[0][tid][0] + stat_sh[1][tid][0];
-      part[mrows + m0 + tid] = stat_sh[0][tid][1] + stat_sh[1][tid][1];
-    }
+    B200_TS();
+    if (alive) epilogue(prev_tile, (it - 1) & 1);
   }
   tc::fence_before_sync();
   __syncthreads();
-  if (warp == 0) tc::tmem_dealloc(tmem_d, BN);
+  if (warp == 0) tc::tmem_dealloc(tmem_d, 2 * BN);
+  if (rec) dbg[127] = nrec;
+#undef B200_TS
 }
+
+long long* tc_debug_buffer();  // tc_gemm.cu
 
 // wt[k][m] = w[m][k]   (w: [rows, cols] row-major)
 __global__ void __launch_bounds__(256)
@@ -244,7 +315,7 @@ static int launch_tc_nt_bn(const NtRows& X, const float* wm, int mrows, const fl
   const int64_t total = (int64_t)m_tiles * ceil_div(n, BN);
   B200_REQUIRE(total < (1ll << 30), B200_E_UNSUPPORTED, "tensor-core linear layer: too many tiles");
   const int grid = (int)(total < num_sms() ? total : num_sms());  // persistent: one CTA per SM
-  kern<<<grid, TNT_THREADS, smem, st>>>(X, wm, mrows, bias, O, colstats, n, m_tiles, (int)total);
+  kern<<<grid, TNT_THREADS, smem, st>>>(X, wm, mrows, bias, O, colstats, n, m_tiles, (int)total, tc_debug_buffer());
   B200_CHECK_LAUNCH("tc_nt_kernel");
   return B200_OK;
 }

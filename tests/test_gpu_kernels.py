@@ -311,7 +311,7 @@ def test_linear_tensor_core_forward_and_input_grad(lib, n, c1, c2, cout):
     y, stats = ops.linear(ag[0], ag[1], ag[2], a2=ag[3] if c2 else None, want_stats=True)
     y.backward(gy.to(DEV))
     assert rel_err(y, y_ref) < 1e-5, rel_err(y, y_ref)  # 3xTF32, tensor-core accumulation over up to 768 terms (fp32 FMA: ~2e-6)
-    assert_close(y, y_ref, atol=2e-5, rtol=1e-5, what="linear y (tcgen05)")
+    assert_close(y, y_ref, atol=3e-6 * (c1 + c2) ** 0.5, rtol=1e-5, what="linear y (tcgen05)")  # K-term sums, |y| up to ~7
     stats = stats.sum(0)
     assert_close(stats[:cout], y_ref.sum(0), atol=1e-3, rtol=1e-5, what="column sums")
     assert_close(stats[cout:], (y_ref ** 2).sum(0), atol=1e-3, rtol=1e-5, what="column sums of squares")
