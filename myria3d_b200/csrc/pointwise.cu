@@ -653,6 +653,81 @@ affine_act_bwd_reduce_kernel(const float* __restrict__ go, const float* __restri
   }
 }
 
+// float4 version (c % 4 == 0): a thread owns 4 channels of every (rows-per-pass)-th row -- 4x fewer load instructions
+// and 4x more bytes in flight per thread than the scalar kernel; the CTA covers c/4 lanes x 256/(c/4) rows per pass.
+__global__ void __launch_bounds__(RED_THREADS)
+affine_act_bwd_reduce_vec4_kernel(const float* __restrict__ go, const float* __restrict__ out, float slope,
+                                  const float* __restrict__ y1, const float* __restrict__ mean1,
+                                  const float* __restrict__ invstd1, double* __restrict__ red1,
+                                  const float* __restrict__ y2, const float* __restrict__ mean2,
+                                  const float* __restrict__ invstd2, double* __restrict__ red2, int64_t n, int c,
+                                  int lanes /* pow2 >= min(c/4, 256) */) {
+  __shared__ float part[12][RED_THREADS];
+  const int tid = threadIdx.x;
+  const int lane = tid % lanes, rsub = tid / lanes, rstep = RED_THREADS / lanes;
+  const int c4 = c >> 2;
+  for (int cbase = 0; cbase < c4; cbase += lanes) {
+    const int q = cbase + lane;  // float4 column
+    float sg[4] = {0.f, 0.f, 0.f, 0.f}, sx1[4] = {0.f, 0.f, 0.f, 0.f}, sx2[4] = {0.f, 0.f, 0.f, 0.f};
+    if (q < c4) {
+      const float4 m1 = __ldg(reinterpret_cast<const float4*>(mean1) + q), is1 = __ldg(reinterpret_cast<const float4*>(invstd1) + q);
+      float4 m2 = make_float4(0.f, 0.f, 0.f, 0.f), is2 = m2;
+      if (y2) m2 = __ldg(reinterpret_cast<const float4*>(mean2) + q), is2 = __ldg(reinterpret_cast<const float4*>(invstd2) + q);
+      const float m1a[4] = {m1.x, m1.y, m1.z, m1.w}, i1a[4] = {is1.x, is1.y, is1.z, is1.w};
+      const float m2a[4] = {m2.x, m2.y, m2.z, m2.w}, i2a[4] = {is2.x, is2.y, is2.z, is2.w};
+      for (int64_t i = (int64_t)blockIdx.x * rstep + rsub; i < n; i += (int64_t)gridDim.x * rstep) {
+        const int64_t off = i * c4 + q;
+        const float4 g4 = __ldg(reinterpret_cast<const float4*>(go) + off);
+        const float4 a4 = __ldg(reinterpret_cast<const float4*>(y1) + off);
+        float g[4] = {g4.x, g4.y, g4.z, g4.w};
+        const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+        if (slope != 1.f) {
+          const float4 o4 = __ldg(reinterpret_cast<const float4*>(out) + off);
+          const float o[4] = {o4.x, o4.y, o4.z, o4.w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) g[u] *= (o[u] > 0.f) ? 1.f : slope;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          sg[u] += g[u];
+          sx1[u] = fmaf(g[u], (a[u] - m1a[u]) * i1a[u], sx1[u]);
+        }
+        if (y2) {
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(y2) + off);
+          const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) sx2[u] = fmaf(g[u], (bb[u] - m2a[u]) * i2a[u], sx2[u]);
+        }
+      }
+    }
+    // per-thread partials -> shared memory (no atomics: CAS-emulated fp64 shared atomics with 32 row groups per address
+    // cost more than the loads), then one thread per output sums its row groups in fp64
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      part[0 + u][tid] = sg[u];
+      part[4 + u][tid] = sx1[u];
+      part[8 + u][tid] = sx2[u];
+    }
+    __syncthreads();
+    for (int t = tid; t < 12 * lanes; t += RED_THREADS) {
+      const int kind = t / (4 * lanes), rem = t % (4 * lanes), ln = rem >> 2, u = rem & 3;
+      const int ch = 4 * (cbase + ln) + u;
+      if (ch >= c || (kind == 2 && !y2)) continue;
+      double acc = 0.0;
+      for (int r = 0; r < rstep; ++r) acc += (double)part[kind * 4 + u][r * lanes + ln];
+      if (kind == 0) {
+        atomicAdd(red1 + ch, acc);
+        if (y2) atomicAdd(red2 + ch, acc);
+      } else if (kind == 1) {
+        atomicAdd(red1 + c + ch, acc);
+      } else {
+        atomicAdd(red2 + c + ch, acc);
+      }
+    }
+    __syncthreads();
+  }
+}
+
 struct BnBranch {
   const float* y;
   const float* gamma;
@@ -903,6 +978,21 @@ extern "C" int b200_affine_act_bwd_reduce(const float* grad_out, const float* ou
   B200_REQUIRE(slope == 1.f || out, B200_E_INVALID, "b200_affine_act_bwd_reduce: activation needs `out`");
   B200_REQUIRE(!y2 || (mean2 && invstd2 && red2), B200_E_INVALID, "b200_affine_act_bwd_reduce: second branch incomplete");
   if (n <= 0) return B200_OK;
+  if (c % 4 == 0 && aligned16(grad_out) && aligned16(y1) && (slope == 1.f || aligned16(out)) && (!y2 || aligned16(y2)) &&
+      aligned16(mean1) && aligned16(invstd1) && (!y2 || (aligned16(mean2) && aligned16(invstd2)))) {
+    int lanes = 1;
+    while (lanes < c / 4 && lanes < RED_THREADS) lanes <<= 1;
+    const int rstep = RED_THREADS / lanes;
+    int64_t blocks = ceil_div(n, (int64_t)rstep * 4);
+    const int64_t cap = (int64_t)num_sms() * 4;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    affine_act_bwd_reduce_vec4_kernel<<<(unsigned)blocks, RED_THREADS, 0,
+                                        static_cast<cudaStream_t>(stream)>>>(grad_out, out, slope, y1, mean1, invstd1, red1, y2,
+                                                                             mean2, invstd2, red2, n, c, lanes);
+    B200_CHECK_LAUNCH("affine_act_bwd_reduce_vec4_kernel");
+    return B200_OK;
+  }
   int lanes = 1;
   while (lanes < c && lanes < RED_THREADS) lanes <<= 1;
   const int rstep = RED_THREADS / lanes;
