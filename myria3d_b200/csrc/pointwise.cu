@@ -578,24 +578,41 @@ __global__ void __launch_bounds__(256)
 affine_act_fwd_kernel(const float* __restrict__ y1, const float* __restrict__ s1, const float* __restrict__ t1,
                       const float* __restrict__ y2, const float* __restrict__ s2, const float* __restrict__ t2,
                       float slope, float* __restrict__ out, int64_t total, int c) {
+  // per-channel (scale, shift) of both branches staged once per CTA: the element loop then reads them with one LDS per
+  // branch and float4 instead of 2-4 global loads per ELEMENT (the kernel was L1-instruction-bound for c >= 128)
+  extern __shared__ __align__(16) float coef[];  // [s1 | t1 | s2 | t2][c]
+  for (int ch = threadIdx.x; ch < c; ch += 256) {
+    coef[ch] = __ldg(s1 + ch);
+    coef[c + ch] = __ldg(t1 + ch);
+    coef[2 * c + ch] = y2 ? __ldg(s2 + ch) : 0.f;
+    coef[3 * c + ch] = y2 ? __ldg(t2 + ch) : 0.f;
+  }
+  __syncthreads();
   for (int64_t idx = ((int64_t)blockIdx.x * 256 + threadIdx.x) * V; idx < total; idx += (int64_t)gridDim.x * 256 * V) {
     const int ch = (int)(idx % c);
-    float a[V], b[V], o[V];
+    float a[V], b[V], o[V], cs1[V], ct1[V], cs2[V], ct2[V];
     if constexpr (V == 4) {
       const float4 v = __ldg(reinterpret_cast<const float4*>(y1 + idx));
       a[0] = v.x, a[1] = v.y, a[2] = v.z, a[3] = v.w;
+      const float4 p = *reinterpret_cast<const float4*>(coef + ch), q = *reinterpret_cast<const float4*>(coef + c + ch);
+      cs1[0] = p.x, cs1[1] = p.y, cs1[2] = p.z, cs1[3] = p.w;
+      ct1[0] = q.x, ct1[1] = q.y, ct1[2] = q.z, ct1[3] = q.w;
       if (y2) {
         const float4 u = __ldg(reinterpret_cast<const float4*>(y2 + idx));
         b[0] = u.x, b[1] = u.y, b[2] = u.z, b[3] = u.w;
+        const float4 p2 = *reinterpret_cast<const float4*>(coef + 2 * c + ch), q2 = *reinterpret_cast<const float4*>(coef + 3 * c + ch);
+        cs2[0] = p2.x, cs2[1] = p2.y, cs2[2] = p2.z, cs2[3] = p2.w;
+        ct2[0] = q2.x, ct2[1] = q2.y, ct2[2] = q2.z, ct2[3] = q2.w;
       }
     } else {
       a[0] = __ldg(y1 + idx);
-      if (y2) b[0] = __ldg(y2 + idx);
+      cs1[0] = coef[ch], ct1[0] = coef[c + ch];
+      if (y2) b[0] = __ldg(y2 + idx), cs2[0] = coef[2 * c + ch], ct2[0] = coef[3 * c + ch];
     }
 #pragma unroll
     for (int u = 0; u < V; ++u) {
-      float v = fmaf(a[u], __ldg(s1 + ch + u), __ldg(t1 + ch + u));
-      if (y2) v += fmaf(b[u], __ldg(s2 + ch + u), __ldg(t2 + ch + u));
+      float v = fmaf(a[u], cs1[u], ct1[u]);
+      if (y2) v += fmaf(b[u], cs2[u], ct2[u]);
       o[u] = lrelu(v, slope);
     }
     if constexpr (V == 4)
@@ -760,9 +777,37 @@ affine_act_bwd_apply_kernel(const float* __restrict__ go, const float* __restric
       }
     }
   }
+  // grad_y = k1 * (g - mg) - k4 * (y - mean) per channel, with k1 = gamma * invstd, mg = red[0]/n, k4 = k1 * invstd *
+  // red[1]/n (train) or k1 = scale, mg = k4 = 0 (eval / plain affine): the four coefficients of both branches are
+  // staged once per CTA (the element loop used 3 global + 2 fp64 loads and 2 fp64 multiplies per ELEMENT)
+  extern __shared__ __align__(16) float coef[];  // [branch][k1 | mg | k4 | mean][c]
+  for (int ch = threadIdx.x; ch < c; ch += 256) {
+#pragma unroll
+    for (int br = 0; br < 2; ++br) {
+      const BnBranch& bb = br == 0 ? b1 : b2;
+      float k1 = 0.f, mg = 0.f, k4 = 0.f, mean = 0.f;
+      if (br == 0 || bb.y) {
+        if (bb.red) {
+          const float is = __ldg(bb.invstd + ch);
+          k1 = __ldg(bb.gamma + ch) * is;
+          mg = (float)(bb.red[ch] * inv_n);
+          k4 = k1 * is * (float)(bb.red[c + ch] * inv_n);
+          mean = __ldg(bb.mean + ch);
+        } else {
+          k1 = __ldg(bb.scale + ch);
+        }
+      }
+      float* t = coef + br * 4 * c;
+      t[ch] = k1, t[c + ch] = mg, t[2 * c + ch] = k4, t[3 * c + ch] = mean;
+    }
+  }
+  __syncthreads();
+  const bool need_y1 = b1.red != nullptr, need_y2 = b2.y && b2.red;
   for (int64_t idx = ((int64_t)blockIdx.x * 256 + threadIdx.x) * V; idx < total; idx += (int64_t)gridDim.x * 256 * V) {
     const int ch0 = (int)(idx % c);
     float g[V], o[V], y1v[V], y2v[V];
+#pragma unroll
+    for (int u = 0; u < V; ++u) y1v[u] = 0.f, y2v[u] = 0.f, o[u] = 1.f;
     if constexpr (V == 4) {
       const float4 a = __ldg(reinterpret_cast<const float4*>(go + idx));
       g[0] = a.x, g[1] = a.y, g[2] = a.z, g[3] = a.w;
@@ -770,44 +815,42 @@ affine_act_bwd_apply_kernel(const float* __restrict__ go, const float* __restric
         const float4 b = __ldg(reinterpret_cast<const float4*>(out + idx));
         o[0] = b.x, o[1] = b.y, o[2] = b.z, o[3] = b.w;
       }
-      if (b1.red) {
+      if (need_y1) {
         const float4 d = __ldg(reinterpret_cast<const float4*>(b1.y + idx));
         y1v[0] = d.x, y1v[1] = d.y, y1v[2] = d.z, y1v[3] = d.w;
       }
-      if (b2.y && b2.red) {
+      if (need_y2) {
         const float4 d = __ldg(reinterpret_cast<const float4*>(b2.y + idx));
         y2v[0] = d.x, y2v[1] = d.y, y2v[2] = d.z, y2v[3] = d.w;
       }
     } else {
       g[0] = __ldg(go + idx);
       if (slope != 1.f) o[0] = __ldg(out + idx);
-      if (b1.red) y1v[0] = __ldg(b1.y + idx);
-      if (b2.y && b2.red) y2v[0] = __ldg(b2.y + idx);
+      if (need_y1) y1v[0] = __ldg(b1.y + idx);
+      if (need_y2) y2v[0] = __ldg(b2.y + idx);
+    }
+    float k[2][4][V];
+#pragma unroll
+    for (int br = 0; br < 2; ++br) {
+      if (br == 1 && !b2.y) break;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float* t = coef + (br * 4 + j) * c + ch0;
+        if constexpr (V == 4) {
+          const float4 q = *reinterpret_cast<const float4*>(t);
+          k[br][j][0] = q.x, k[br][j][1] = q.y, k[br][j][2] = q.z, k[br][j][3] = q.w;
+        } else {
+          k[br][j][0] = t[0];
+        }
+      }
     }
     float r1[V], r2[V];
 #pragma unroll
     for (int u = 0; u < V; ++u) {
-      const int ch = ch0 + u;
       float gg = g[u];
       if (slope != 1.f) gg *= (o[u] > 0.f) ? 1.f : slope;
-      if (b1.red) {
-        const float is = __ldg(b1.invstd + ch);
-        const float xh = (y1v[u] - __ldg(b1.mean + ch)) * is;
-        const float mg = (float)(b1.red[ch] * inv_n), mgx = (float)(b1.red[c + ch] * inv_n);
-        r1[u] = __ldg(b1.gamma + ch) * is * (gg - mg - xh * mgx);
-      } else {
-        r1[u] = gg * __ldg(b1.scale + ch);
-      }
-      if (b2.y) {
-        if (b2.red) {
-          const float is = __ldg(b2.invstd + ch);
-          const float xh = (y2v[u] - __ldg(b2.mean + ch)) * is;
-          const float mg = (float)(b2.red[ch] * inv_n), mgx = (float)(b2.red[c + ch] * inv_n);
-          r2[u] = __ldg(b2.gamma + ch) * is * (gg - mg - xh * mgx);
-        } else {
-          r2[u] = gg * __ldg(b2.scale + ch);
-        }
-      }
+      r1[u] = k[0][0][u] * (gg - k[0][1][u]) - k[0][2][u] * (y1v[u] - k[0][3][u]);
+      if (b2.y) r2[u] = k[1][0][u] * (gg - k[1][1][u]) - k[1][2][u] * (y2v[u] - k[1][3][u]);
     }
     if constexpr (V == 4) {
       *reinterpret_cast<float4*>(b1.grad_y + idx) = make_float4(r1[0], r1[1], r1[2], r1[3]);
@@ -958,14 +1001,15 @@ extern "C" int b200_affine_act_fwd(const float* y1, const float* scale1, const f
                                    int32_t c, void* stream) {
   B200_REQUIRE(y1 && scale1 && shift1 && out && c > 0, B200_E_INVALID, "b200_affine_act_fwd: null pointer");
   B200_REQUIRE(!y2 || (scale2 && shift2), B200_E_INVALID, "b200_affine_act_fwd: second branch incomplete");
+  B200_REQUIRE(c <= 2048, B200_E_UNSUPPORTED, "b200_affine_act_fwd: at most 2048 channels (per-CTA coefficient table)");
   if (n <= 0) return B200_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int64_t total = n * c;
   const bool vec = (c % 4 == 0) && aligned16(y1) && aligned16(out) && (!y2 || aligned16(y2));
   if (vec)
-    affine_act_fwd_kernel<4><<<elementwise_grid(total / 4), 256, 0, st>>>(y1, scale1, shift1, y2, scale2, shift2, slope, out, total, c);
+    affine_act_fwd_kernel<4><<<elementwise_grid(total / 4), 256, 4 * c * sizeof(float), st>>>(y1, scale1, shift1, y2, scale2, shift2, slope, out, total, c);
   else
-    affine_act_fwd_kernel<1><<<elementwise_grid(total), 256, 0, st>>>(y1, scale1, shift1, y2, scale2, shift2, slope, out, total, c);
+    affine_act_fwd_kernel<1><<<elementwise_grid(total), 256, 4 * c * sizeof(float), st>>>(y1, scale1, shift1, y2, scale2, shift2, slope, out, total, c);
   B200_CHECK_LAUNCH("affine_act_fwd_kernel");
   return B200_OK;
 }
@@ -1021,6 +1065,7 @@ extern "C" int b200_affine_act_bwd_apply(const float* grad_out, const float* out
                "b200_affine_act_bwd_apply: branch 2 incomplete");
   B200_REQUIRE((grad_gamma1 == nullptr) == (grad_beta1 == nullptr) && (grad_gamma2 == nullptr) == (grad_beta2 == nullptr),
                B200_E_INVALID, "b200_affine_act_bwd_apply: grad_gamma / grad_beta must come together");
+  B200_REQUIRE(c <= 1024, B200_E_UNSUPPORTED, "b200_affine_act_bwd_apply: at most 1024 channels (per-CTA coefficient table)");
   if (n <= 0) return B200_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   BnBranch b1{y1, gamma1, mean1, invstd1, red1, scale1, grad_y1, grad_gamma1, grad_beta1};
@@ -1029,9 +1074,9 @@ extern "C" int b200_affine_act_bwd_apply(const float* grad_out, const float* out
   bool vec = (c % 4 == 0) && aligned16(grad_out) && aligned16(grad_y1) && (!out || aligned16(out)) &&
              (!y1 || aligned16(y1)) && (!y2 || (aligned16(y2) && aligned16(grad_y2)));
   if (vec)
-    affine_act_bwd_apply_kernel<4><<<elementwise_grid(total / 4), 256, 0, st>>>(grad_out, out, slope, b1, b2, n, c);
+    affine_act_bwd_apply_kernel<4><<<elementwise_grid(total / 4), 256, 8 * c * sizeof(float), st>>>(grad_out, out, slope, b1, b2, n, c);
   else
-    affine_act_bwd_apply_kernel<1><<<elementwise_grid(total), 256, 0, st>>>(grad_out, out, slope, b1, b2, n, c);
+    affine_act_bwd_apply_kernel<1><<<elementwise_grid(total), 256, 8 * c * sizeof(float), st>>>(grad_out, out, slope, b1, b2, n, c);
   B200_CHECK_LAUNCH("affine_act_bwd_apply_kernel");
   return B200_OK;
 }
