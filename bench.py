@@ -72,7 +72,7 @@ def peaks():
 def host_batch(tiles: int, points: int, seed: int):
     """Synthetic 50 m x 50 m Lidar-HD-like tiles as a pinned host Batch."""
     from myria3d_b200 import Batch, Data
-    from oracle.randla_oracle import synthetic_tile  # data generator only (not a compute path)
+    from myria3d_b200.synthetic import synthetic_tile
 
     datas = []
     for t in range(tiles):

@@ -9,7 +9,7 @@ import numpy as np
 import torch
 from myria3d_b200 import Batch, Data, Model, ops
 from myria3d_b200.interpolation import Interpolator
-from oracle.randla_oracle import synthetic_tile  # synthetic data generator only
+from myria3d_b200.synthetic import synthetic_tile
 
 dev = torch.device("cuda", 0)
 CLASSES = {1: "unclassified", 2: "ground", 6: "building", 9: "water", 17: "bridge", 64: "lasting_above"}

@@ -9,7 +9,7 @@ import argparse, os, sys, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from ctypes import c_void_p
-from oracle.randla_oracle import synthetic_batch
+from myria3d_b200.synthetic import synthetic_batch
 from myria3d_b200 import _lib, ops
 from myria3d_b200.ops import _p, _stream
 

@@ -166,3 +166,29 @@ def test_fused_decimation_is_a_valid_draw():
     for _ in range(200):
         hits[fused_decimation_indices(lvl, new_ptr)[:250]] += 1
     assert abs(float(hits.mean()) - 50.0) < 1e-6 and float(hits.std()) < 9.0
+
+
+def test_synthetic_workload_matches_the_oracle_copy():
+    """bench.py draws its tiles from myria3d_b200.synthetic (no oracle import on the GPU arm); the CPU reference arm and
+    the tests use the oracle's copy: same seeds must give the same tensors, bit for bit."""
+    import torch
+
+    from myria3d_b200 import synthetic as S
+    from oracle import randla_oracle as O
+
+    for a, b in zip(S.synthetic_batch([700, 33], seed=4242), O.synthetic_batch([700, 33], seed=4242)):
+        assert torch.equal(a, b)
+
+
+def test_product_never_imports_the_oracle():
+    """The package, bench.py's GPU arm and the scripts must not depend on oracle/ (test infrastructure)."""
+    import pathlib
+    import re as _re
+
+    root = pathlib.Path(__file__).resolve().parents[1]
+    for path in list((root / "myria3d_b200").glob("*.py")):
+        assert not _re.search(r"^\s*(from|import)\s+oracle", path.read_text(), _re.M), path
+    bench = (root / "bench.py").read_text()
+    hits = [m.start() for m in _re.finditer(r"^\s*(from|import)\s+oracle", bench, _re.M)]
+    assert len(hits) == 1  # cpu_reference() only: the cpu_baseline leg and --impl reference
+    assert "def cpu_reference" in bench[:hits[0]] and "def run_reference" not in bench[:hits[0]]
