@@ -381,6 +381,18 @@ struct LfaBwdPlan {
   // dW[n][:] += da[k][n] * F[k][:] needs only broadcast LDS.128 of the centre's F rows (16 FMA per load) instead of
   // the 4x4-block GEMM3 whose strided row reads were 4-way bank conflicted and shared-memory bound.
   static constexpr bool DW_BY_CENTRE = (C <= 32);
+  // Encoder-gradient partials in shared memory (C >= 64): one private [H][8] slab per group of threads in which every
+  // encoder column has exactly ONE writer after an intra-warp shuffle reduction over the centres of the warp --
+  // plain read-modify-write instead of contended float atomics (sm_100a emulates shared float atomicAdd with a CAS
+  // loop: 37 M excess shared wavefronts out of 85 M in the c = 64 kernel, profiles/ncu_lfa_bwd64b_r01.summary.txt).
+  static constexpr int GE_GROUP = (Cfg::TPC > 32) ? Cfg::TPC : 32;     // threads sharing a slab
+  static constexpr int GE_SLABS = GE_IN_REGS ? 1 : (THREADS / GE_GROUP);
+  __host__ __device__ static constexpr unsigned enc_lane_mask() {  // lanes of a warp whose columns lie in the encoder half
+    unsigned m = 0;
+    for (int l = 0; l < 32; ++l)
+      if (((l % Cfg::TPC) * Cfg::CW) >= Cfg::H || Cfg::TPC > 32) m |= 1u << l;
+    return m;
+  }
 };
 
 template <class Cfg, bool SPLIT_DW>
@@ -402,12 +414,12 @@ lfa_bwd_kernel(const float* __restrict__ x, const float* __restrict__ pos, const
   float4* Q = reinterpret_cast<float4*>(DA + Cfg::TILE_FLOATS);
   float4* P = Q + EDGES;
   int* NB = reinterpret_cast<int*>(P + TC);
-  float* GE = reinterpret_cast<float*>(NB + EDGES);  // [H][8]: 7 weight grads + bias grad
+  float* GE = reinterpret_cast<float*>(NB + EDGES);  // [GE_SLABS][H][8]: 7 weight grads + bias grad
 
   const int tid = threadIdx.x;
   const int g = tid / TPC, col0 = (tid % TPC) * CW;
 
-  for (int t = tid; t < H * 8; t += THREADS) GE[t] = 0.f;
+  for (int t = tid; t < Plan::GE_SLABS * H * 8; t += THREADS) GE[t] = 0.f;
 
   constexpr int DWP = SPLIT_DW ? 1 : Plan::PASSES;
   float dw[DWP][16];
@@ -557,9 +569,23 @@ lfa_bwd_kernel(const float* __restrict__ x, const float* __restrict__ pos, const
 #pragma unroll
           for (int t = 0; t < 8; ++t) ge_reg[cw][t] += gw[t];
         } else {
-          float* ge = GE + (col0 - H + cw) * 8;
+          // sum over the centres that share this warp (lanes l, l ^ TPC, ... hold the same columns), then the first
+          // of them adds into the slab of its thread group: one writer per address, no atomics
+          if constexpr (TPC < 32) {
+            constexpr unsigned kMask = Plan::enc_lane_mask();
 #pragma unroll
-          for (int t = 0; t < 8; ++t) atomicAdd(ge + t, gw[t]);
+            for (int off = TPC; off < 32; off <<= 1)
+#pragma unroll
+              for (int t = 0; t < 8; ++t) gw[t] += __shfl_xor_sync(kMask, gw[t], off);
+          }
+          if ((tid & 31) < TPC || TPC >= 32) {
+            float* ge = GE + ((tid / Plan::GE_GROUP) * H + (col0 - H + cw)) * 8;
+            float4 a = *reinterpret_cast<float4*>(ge), b = *reinterpret_cast<float4*>(ge + 4);
+            a.x += gw[0], a.y += gw[1], a.z += gw[2], a.w += gw[3];
+            b.x += gw[4], b.y += gw[5], b.z += gw[6], b.w += gw[7];
+            *reinterpret_cast<float4*>(ge) = a;
+            *reinterpret_cast<float4*>(ge + 4) = b;
+          }
         }
       }
     }
@@ -633,7 +659,9 @@ lfa_bwd_kernel(const float* __restrict__ x, const float* __restrict__ pos, const
   }
   __syncthreads();
   for (int t = tid; t < H * 8; t += THREADS) {
-    const float v = GE[t];
+    float v = 0.f;
+#pragma unroll
+    for (int sl = 0; sl < Plan::GE_SLABS; ++sl) v += GE[sl * H * 8 + t];
     const int m = t >> 3, s = t & 7;
     if (s < 7)
       atomicAdd(grad_enc_w + m * 7 + s, v);
@@ -652,7 +680,7 @@ static size_t lfa_fwd_smem() {
 template <class Cfg>
 static size_t lfa_bwd_smem() {
   return sizeof(float) * 2 * Cfg::TILE_FLOATS + sizeof(float4) * (Cfg::EDGES + Cfg::TC) + sizeof(int) * Cfg::EDGES +
-         sizeof(float) * Cfg::H * 8;
+         sizeof(float) * LfaBwdPlan<Cfg>::GE_SLABS * Cfg::H * 8;
 }
 
 static int persistent_grid(const void* kernel, int threads, size_t smem, int64_t ntiles) {
