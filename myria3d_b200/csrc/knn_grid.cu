@@ -206,7 +206,7 @@ struct TopKLex {
 };
 
 template <int KMAX, bool SELF>
-__global__ void __launch_bounds__(GRID_THREADS)
+__global__ void __launch_bounds__(GRID_THREADS, (KMAX <= 16 ? 4 : 1))
 knn_grid_kernel(const float4* __restrict__ sorted, const int* __restrict__ starts, const GridMeta* __restrict__ meta,
                 const int64_t* __restrict__ ptr_x, const float* __restrict__ pos_y, const int64_t* __restrict__ ptr_y,
                 int stride, int k, int kt, int32_t* __restrict__ nbr, float* __restrict__ dist2) {
@@ -238,23 +238,32 @@ knn_grid_kernel(const float4* __restrict__ sorted, const int* __restrict__ start
     const float qb = (m.db == 0) ? q[0] : ((m.db == 1) ? q[1] : q[2]);
     const int ca = grid_cell_1d(qa, m.oa, m.inva, g), cb = grid_cell_1d(qb, m.ob, m.invb, g);
 
-    auto scan = [&](int s, int e) {
-      for (int u = s; u < e; ++u) {
-        const float4 c = __ldg(pts + u);
-        top.push(dist2_rn(c.x, c.y, c.z, q[0], q[1], q[2]), __float_as_int(c.w));
-      }
-    };
-
     for (int r = 0;; ++r) {
       const int a0 = ca - r, a1 = ca + r, b0 = cb - r, b1 = cb + r;
       const int alo = a0 < 0 ? 0 : a0, ahi = a1 > g - 1 ? g - 1 : a1;
       const int blo = b0 < 0 ? 0 : b0, bhi = b1 > g - 1 ? g - 1 : b1;
       for (int bb = blo; bb <= bhi; ++bb) {
-        if (bb == b0 || bb == b1) {
-          scan(st[bb * g + alo], st[bb * g + ahi + 1]);  // a whole ring row: one contiguous run
+        // Every lane runs the SAME two candidate loops with its own ranges (empty where not needed): run 1 = the whole
+        // ring row (a contiguous run of the sorted array) or the left cell of an interior row, run 2 = the right cell of
+        // an interior row.  Separate call sites per case made the lanes of a warp -- neighbouring queries whose rings
+        // are shifted by a cell -- take different code paths: 9 of 32 lanes active in the distance evaluation
+        // (profiles/ncu_knn_grid_r01.summary.txt).
+        const bool full = (bb == b0 || bb == b1);
+        const int* row = st + bb * g;
+        int s1 = 0, e1 = 0, s2 = 0, e2 = 0;
+        if (full) {
+          s1 = row[alo], e1 = row[ahi + 1];
         } else {
-          if (a0 >= 0) scan(st[bb * g + a0], st[bb * g + a0 + 1]);
-          if (a1 <= g - 1) scan(st[bb * g + a1], st[bb * g + a1 + 1]);
+          if (a0 >= 0) s1 = row[a0], e1 = row[a0 + 1];
+          if (a1 <= g - 1) s2 = row[a1], e2 = row[a1 + 1];
+        }
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+          const int s = pass ? s2 : s1, e = pass ? e2 : e1;
+          for (int u = s; u < e; ++u) {
+            const float4 c = __ldg(pts + u);
+            top.push(dist2_rn(c.x, c.y, c.z, q[0], q[1], q[2]), __float_as_int(c.w));
+          }
         }
       }
       if (a0 <= 0 && a1 >= g - 1 && b0 <= 0 && b1 >= g - 1) break;  // the whole grid has been visited
