@@ -30,6 +30,7 @@ class _Captured:
         self.static: Dict[str, Tensor] = {}
         self.idx_static: List[Tensor] = []
         self.idx_next: Optional[List[Tensor]] = None
+        self.draws_in_graph = False
         self.loss: Optional[Tensor] = None
         self.logits: Optional[Tensor] = None
         self.ptr_host: List[int] = []
@@ -82,7 +83,11 @@ class GraphedTrainStep:
         for k in ("x", "pos", "y", "batch", "ptr"):
             cap.static[k] = getattr(batch, k).to(dev, non_blocking=True).clone()
         levels = self.net.levels_for(cap.ptr_host, dev)
-        cap.idx_static = self._draw_decimation(levels)
+        # "fused" draws (randint + sort + gather per level) are graph-safe: they are captured with the step, every
+        # replay advances the Philox offset and draws fresh subsets -- no eager launches between replays.  The
+        # reference's per-cloud randperm stream stays outside the graph and enters through static index buffers.
+        cap.draws_in_graph = self.net.decimation_rng == "fused"
+        cap.idx_static = None if cap.draws_in_graph else self._draw_decimation(levels)
         multi = self.reducer is not None and self.reducer.world_size > 1
 
         prev_static, prev_inj = self.net.static_ptr_host, self.net.injected_decimation_idx
@@ -110,6 +115,8 @@ class GraphedTrainStep:
                     self.optimizer.step()
                 cap.loss = out["loss"].detach()
                 cap.logits = out["logits"].detach()
+                if cap.draws_in_graph:  # the subsets of the last replay (static tensors owned by the graph)
+                    cap.idx_static = list(self.net.last_decimation_idx)
             cap.launches_per_step = _lib.launch_count() - n0
             if multi:
                 cap.opt_graph = torch.cuda.CUDAGraph()
@@ -139,17 +146,19 @@ class GraphedTrainStep:
             cap = self._captured[key] = self._capture(batch)
         for k in ("x", "pos", "y", "batch"):
             cap.static[k].copy_(getattr(batch, k), non_blocking=True)
-        levels = self.net.levels_for(cap.ptr_host, self.device)
-        idx = cap.idx_next if cap.idx_next is not None else self._draw_decimation(levels)
-        for dst, src in zip(cap.idx_static, idx):
-            dst.copy_(src, non_blocking=True)
+        if not cap.draws_in_graph:
+            levels = self.net.levels_for(cap.ptr_host, self.device)
+            idx = cap.idx_next if cap.idx_next is not None else self._draw_decimation(levels)
+            for dst, src in zip(cap.idx_static, idx):
+                dst.copy_(src, non_blocking=True)
         cap.graph.replay()
         if cap.opt_graph is not None:
             self.reducer.all_reduce()
             cap.opt_graph.replay()
         self.library_launches += cap.launches_per_step
-        # draw the next step's subsets now: the launches hide behind the replay that was just enqueued
-        cap.idx_next = self._draw_decimation(levels)
+        if not cap.draws_in_graph:
+            # draw the next step's subsets now: the launches hide behind the replay that was just enqueued
+            cap.idx_next = self._draw_decimation(levels)
         return cap.loss
 
     def last_outputs(self, batch) -> Dict[str, Tensor]:
