@@ -192,3 +192,44 @@ def test_product_never_imports_the_oracle():
     hits = [m.start() for m in _re.finditer(r"^\s*(from|import)\s+oracle", bench, _re.M)]
     assert len(hits) == 1  # cpu_reference() only: the cpu_baseline leg and --impl reference
     assert "def cpu_reference" in bench[:hits[0]] and "def run_reference" not in bench[:hits[0]]
+
+
+def test_fused_decimation_many_clouds_uses_wide_keys():
+    """More than 32 clouds: the (cloud id, random bits) key no longer fits 31 bits -> int64 keys, same guarantees."""
+    from myria3d_b200.randla_net import _Level, decimation_sizes, fused_decimation_indices
+
+    sizes = [37 + (i % 5) for i in range(40)]
+    ptr = [0]
+    for n in sizes:
+        ptr.append(ptr[-1] + n)
+    lvl = _Level(ptr, torch.device("cpu"))
+    new_ptr = decimation_sizes(ptr, 4)
+    shift, take, bits = lvl.decimation_tables(new_ptr)
+    assert shift.dtype == torch.int64 and bits == 31
+    idx = fused_decimation_indices(lvl, new_ptr)
+    for b in range(40):
+        part = idx[new_ptr[b]:new_ptr[b + 1]]
+        assert part.numel() == max(1, sizes[b] // 4)
+        assert ((part >= ptr[b]) & (part < ptr[b + 1])).all() and part.unique().numel() == part.numel()
+    small = _Level([0, 10, 30], torch.device("cpu"))
+    s32, _, bits32 = small.decimation_tables(decimation_sizes([0, 10, 30], 4))
+    assert s32.dtype == torch.int32 and bits32 == 30 and int(s32.max()) == 1 << 30
+
+
+def test_scratch_arena_hands_out_zeroed_disjoint_slices():
+    """ops._ScratchArena (small zero-initialised reduction buffers of the backward pass): aligned disjoint slices, None when
+    full (callers then fall back to torch.zeros), one clear per reset."""
+    from myria3d_b200.ops import _ScratchArena
+
+    a = _ScratchArena(torch.device("cpu"), nbytes=256)
+    x = a.take(5, torch.float64)   # 40 -> 48 bytes
+    y = a.take(3, torch.float32)   # 12 -> 16 bytes
+    assert x.dtype == torch.float64 and x.numel() == 5 and y.numel() == 3 and a.off == 64
+    assert x.data_ptr() % 16 == 0 and y.data_ptr() % 16 == 0 and y.data_ptr() - x.data_ptr() == 48
+    x.fill_(7.0), y.fill_(3.0)
+    assert a.take(100, torch.float32) is None  # would overflow: no partial hand-out
+    assert a.off == 64
+    a.reset()
+    assert a.off == 0 and not a.buf.any()
+    z = a.take(5, torch.float64)
+    assert z.data_ptr() == x.data_ptr() and not z.any()
