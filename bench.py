@@ -303,7 +303,8 @@ def workload_config(args, world, impl="b200"):
     return {
         "workload": f"RandLA-Net full (4 down/4 up), K={K_NEIGHBORS}, {args.points} pts/tile, batch={args.tiles}/GPU "
                     f"(BASELINE configs[1]{'/[2]' if world > 1 else ''})",
-        "optimizer": "torch.optim.Adam(fused)" if getattr(args, "torch_adam", False) else "FlatAdam (b200_adam_flat)",
+        "optimizer": ("torch.optim.Adam (CPU)" if impl == "reference" else
+                      "torch.optim.Adam(fused)" if getattr(args, "torch_adam", False) else "FlatAdam (b200_adam_flat)"),
         "step": "fwd + CrossEntropyLoss + bwd + flat NCCL grad all-reduce (N>1) + Adam; "
                 + ("reference CPU path: eager PyTorch, bounded sample of "
                    f"{args.cpu_tiles} tiles per step" if impl == "reference" else
