@@ -264,3 +264,27 @@ def test_param_grads_accumulate_into_existing_buffers(lib):
         scale = float(first[n_].abs().max())
         # (biases in front of a BatchNorm have a mathematically zero gradient: fp32 noise, different on every run)
         assert_close(p.grad, 2 * first[n_], atol=2e-5 * scale + 1e-6 * top, what=f"accumulated grad of {n_}")
+
+
+def test_against_trained_checkpoint_golden(lib):
+    """CUDA path under the reference's shipped, TRAINED weights (tests/golden/randla_trained_ckpt.pt, generated by
+    oracle/gen_golden_ckpt.py from trained_model_assets/proto151_V2.0_epoch_100_Myria3DV3.1.0.ckpt): strict state-dict
+    load, eval-mode logits within 1e-3 of the fp64 oracle (logit magnitudes up to 22 here; the fp32 oracle itself is
+    4e-5 away) and identical predicted classes."""
+    import os
+
+    from myria3d_b200 import B200RandLANet
+    from myria3d_b200.synthetic import synthetic_batch
+
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "randla_trained_ckpt.pt"))
+    net = B200RandLANet(g["num_features"], g["num_classes"], num_neighbors=g["k"], return_logits=True)
+    net.load_state_dict(g["state_dict"], strict=True)
+    net.to(DEV).eval()
+    x, pos, _, batch, ptr = synthetic_batch(g["sizes"], seed=g["seed"], num_features=9, num_classes=7)
+    net.injected_decimation_idx = g["decimation_idx"]
+    with torch.no_grad():
+        logits = net(x.to(DEV), pos.to(DEV), batch.to(DEV), ptr.to(DEV))
+    tol = max(LOGIT_TOL, 10 * g["fp32_vs_fp64_max_err"])
+    assert_close(logits, g["logits_fp64"], atol=tol, what="eval logits vs trained-checkpoint golden (fp64 oracle)")
+    agree = (logits.argmax(1).cpu() == g["logits_fp64"].argmax(1)).float().mean()
+    assert float(agree) >= 0.999, float(agree)
