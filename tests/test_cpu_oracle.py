@@ -183,3 +183,50 @@ def test_oracle_matches_trained_checkpoint_golden():
     assert_close(logits, g["logits_fp32"], atol=2e-5, what="oracle logits vs trained-checkpoint golden")
     assert_close(logits, g["logits_fp64"], atol=1e-4 + 10 * g["fp32_vs_fp64_max_err"], what="fp32 oracle vs fp64 oracle")
     assert float(g["logits_fp32"].abs().max()) > 10.0  # realistic magnitudes, unlike the random-init fixtures
+
+
+def test_oracle_tiles_of_a_batch_are_independent_in_eval_mode():
+    """pyg_randla_net.py:180,216-229,250: kNN, decimation and interpolation are per cloud, BatchNorm uses running
+    statistics in eval mode -> the logits of a tile do not depend on what else is in the batch (same subsets)."""
+    torch.manual_seed(5)
+    net = build_net(seed=77)
+    net.eval()
+    sizes = [600, 350, 90]
+    x, pos, _, batch, ptr = O.synthetic_batch(sizes, seed=31)
+    with torch.no_grad():
+        full = net(x, pos, batch, ptr)
+        idx = [t.clone() for t in net.last_decimation_idx]
+        # tile 1 alone, with its own share of every level's subset (cloud-local indices)
+        lo, hi = int(ptr[1]), int(ptr[2])
+        sub_idx, lvl_ptr = [], [int(v) for v in ptr]
+        for t in idx:
+            nxt = [0]
+            for b in range(len(lvl_ptr) - 1):
+                nxt.append(nxt[-1] + max(1, (lvl_ptr[b + 1] - lvl_ptr[b]) // 4))
+            sub_idx.append(t[nxt[1]:nxt[2]] - lvl_ptr[1])
+            lvl_ptr = nxt
+        alone = net(x[lo:hi], pos[lo:hi], torch.zeros(hi - lo, dtype=torch.int64), torch.tensor([0, hi - lo]),
+                    decimation_idx=sub_idx)
+    assert_close(alone, full[lo:hi], atol=2e-5, what="tile alone vs tile inside a batch")
+
+
+def test_oracle_attentive_pooling_identities():
+    """LocalFeatureAggregation.message (:126-152): per centre and channel the softmax weights sum to 1 (up to the 1e-16
+    of PyG's softmax), so with W_att = 0 the pooled feature is the neighbourhood MEAN of f; and a cloud smaller than K
+    only ever sees its own points."""
+    n, k = 40, 16
+    g = torch.Generator().manual_seed(2)
+    pos = torch.rand(n, 3, generator=g)
+    ptr = [0, 9, n]  # first cloud has 9 < K points
+    ei = O.knn_graph(pos, k, ptr, method="brute")
+    src, dst = ei[0], ei[1]
+    assert ((src < 9) == (dst < 9)).all()  # edges never cross clouds
+    deg = torch.bincount(dst, minlength=n)
+    assert deg[:9].eq(9).all() and deg[9:].eq(k).all()
+    f = torch.randn(ei.shape[1], 6, generator=g)
+    att = torch.zeros_like(f)  # W_att = 0 -> uniform attention
+    s = O.pyg_softmax(att, dst, n)
+    assert_close(O.scatter_sum(s, dst, n), torch.ones(n, 6), atol=1e-6, what="softmax weights sum to one")
+    pooled = O.scatter_sum(s * f, dst, n)
+    mean = O.scatter_sum(f, dst, n) / deg[:, None]
+    assert_close(pooled, mean, atol=1e-6, what="uniform attention = neighbourhood mean")
