@@ -59,7 +59,9 @@ int b200_knn(const float* pos_x, const int64_t* ptr_x, int64_t nx,
              int32_t num_clouds, int64_t max_queries_per_cloud,
              int32_t k, int32_t kt, int32_t* nbr, float* dist2, void* stream);
 
-/* Same contract and bit-identical output as b200_knn, but each query only visits the cells of a per-cloud
+/* Replaces the same reference calls as b200_knn (knn_graph, pyg_randla_net.py:180; knn inside knn_interpolate,
+ * pyg_randla_net.py:250, models/model.py:90).
+ * Same contract and bit-identical output as b200_knn, but each query only visits the cells of a per-cloud
  * uniform 2-D bucket grid (over the two widest axes) that can still contain one of its k nearest
  * neighbours: O(n k) instead of O(n^2) distance evaluations.  Needs a caller-owned, 256-byte aligned
  * workspace of b200_knn_grid_workspace_bytes(nx, num_clouds, max_x_per_cloud) bytes (contents are
@@ -106,7 +108,9 @@ int b200_encoder_fold_bwd(const float* w, const float* b, const float* gamma, co
                           float* grad_w, float* grad_b, float* grad_gamma, float* grad_beta,
                           int32_t h, int32_t accumulate, void* stream);
 
-/* Fused forward.  c = channels of the LFA (x has h = c/2 features).
+/* Fused forward of LocalFeatureAggregation.propagate()+message() (pyg_randla_net.py:121-152: x_j / pos gathers :121-124,
+ * relative position encoding :141-143, mlp_encoder :144, concat :145, mlp_attention :149, softmax :150, weighting :152,
+ * aggr="add").  c = channels of the LFA (x has h = c/2 features).
  *   x       fp32 [n, h]        pos fp32 [n, 3]      nbr int32 [n, kt]
  *   enc_w   fp32 [h, 7]        encoder weight acting on q=(p_i,p_j,dist), BatchNorm folded in
  *   enc_b   fp32 [h]           folded bias
@@ -117,7 +121,8 @@ int b200_lfa_fwd(const float* x, const float* pos, const int32_t* nbr,
                  const float* enc_w, const float* enc_b, const float* att_wt,
                  float* out, int64_t n, int32_t c, int32_t kt, void* stream);
 
-/* Fused backward (recomputes the forward per tile).  grad_x / grad_enc_w / grad_enc_b /
+/* Fused backward of the same block (autograd of pyg_randla_net.py:121-152; recomputes the forward per tile).
+ * grad_x / grad_enc_w / grad_enc_b /
  * grad_att_w are ACCUMULATED into (atomics): the caller zero-fills them.
  *   att_w   fp32 [c, c]  mlp_attention.lins.0.weight as stored ([out, in])
  *   grad_att_w fp32 [c, c] in the same [out, in] layout
@@ -177,7 +182,8 @@ int64_t b200_linear_fwd_num_stat_partials(int64_t n, int32_t c1, int32_t c2, int
 int b200_linear_fwd(const float* a1, int64_t ld1, int32_t c1, const float* a2, int64_t ld2, int32_t c2,
                     const float* w, const float* bias, float* y, int64_t n, int32_t cout,
                     double* colstats, void* stream);
-/* grad_a[n, c1+c2 split as ga1|ga2] = grad_y W ; either output may be NULL (skipped).
+/* Autograd of the Linear layers of SharedMLP / fc0 / fc_classif (pyg_randla_net.py:42,53,97-109), input side:
+ * grad_a[n, c1+c2 split as ga1|ga2] = grad_y W ; either output may be NULL (skipped).
  * workspace (16-byte aligned, b200_linear_bwd_input_workspace_bytes(), may be NULL / 0): holds W^T for the
  * tensor-core path (layers with >= 64 input and output channels); without it the fp32-FMA kernel runs.
  * Layers with >= 64 input and output channels (and c1 % 32 == 0) run on tcgen05 (3xTF32) in b200_linear_fwd /
@@ -186,7 +192,8 @@ int64_t b200_linear_bwd_input_workspace_bytes(int64_t n, int32_t c1, int32_t c2,
 int b200_linear_bwd_input(const float* grad_y, const float* w, float* ga1, int64_t ldg1, int32_t c1,
                           float* ga2, int64_t ldg2, int32_t c2, void* workspace, int64_t workspace_bytes,
                           int64_t n, int32_t cout, void* stream);
-/* grad_w[cout, c1+c2] += grad_y^T [a1|a2];  grad_bias[cout] += column sums of grad_y
+/* Autograd of the same Linear layers (pyg_randla_net.py:42,53,97-109), parameter side:
+ * grad_w[cout, c1+c2] += grad_y^T [a1|a2];  grad_bias[cout] += column sums of grad_y
  * (both ACCUMULATED: caller zero-fills; grad_bias may be NULL).  >= 64 x 64 weights run on the tensor cores
  * (tcgen05, 3xTF32 split: fp32-grade accuracy).  `workspace` (optional; 16-byte aligned,
  * b200_linear_bwd_weight_workspace_bytes() bytes) lets the split-K partial tiles be reduced by a second
@@ -197,7 +204,8 @@ int b200_linear_bwd_weight(const float* grad_y, const float* a1, int64_t ld1, in
                            float* grad_w, float* grad_bias, void* workspace, int64_t workspace_bytes,
                            int64_t n, int32_t cout, void* stream);
 
-/* BatchNorm statistics -> per-channel affine.  colstats fp64 [num_partials, 2*c] = partial (sum, sum of
+/* BatchNorm1d(momentum 0.01, eps 1e-6) of SharedMLP (pyg_randla_net.py:94-109; PyG MLP norm="batch_norm"):
+ * statistics -> per-channel affine.  colstats fp64 [num_partials, 2*c] = partial (sum, sum of
  * squares) rows that add up to the statistics over `count` rows.  Writes scale = gamma*invstd, shift = beta - mean*scale, and
  * mean / invstd (saved for backward).  If running_mean != NULL updates the running
  * statistics in place: r = (1-momentum) r + momentum * stat (unbiased variance).
@@ -208,18 +216,21 @@ int b200_bn_finalize(const double* colstats, int32_t num_partials, int64_t count
                      float momentum, float eps,
                      float* scale, float* shift, float* mean, float* invstd, int32_t c, void* stream);
 
-/* out = act(y1*scale1 + shift1 [+ y2*scale2 + shift2]) ; act = LeakyReLU(slope) (slope = 1: identity). */
+/* BatchNorm apply + LeakyReLU(0.2) of SharedMLP (pyg_randla_net.py:92,97-109) and, with the second branch, the residual
+ * tail lrelu(mlp2(x) + shortcut(x)) of DilatedResidualBlock (pyg_randla_net.py:186-187):
+ * out = act(y1*scale1 + shift1 [+ y2*scale2 + shift2]) ; act = LeakyReLU(slope) (slope = 1: identity). */
 int b200_affine_act_fwd(const float* y1, const float* scale1, const float* shift1,
                         const float* y2, const float* scale2, const float* shift2,
                         float slope, float* out, int64_t n, int32_t c, void* stream);
 
-/* Backward, pass 1: g = grad_out * act'(out); accumulates (fp64, pre-zeroed)
+/* Backward of the same block (autograd of pyg_randla_net.py:97-109,186-187), pass 1: g = grad_out * act'(out);
+ * accumulates (fp64, pre-zeroed)
  *   red1[0:c] = sum g,  red1[c:2c] = sum g * (y1 - mean1) * invstd1   (and red2 likewise for y2). */
 int b200_affine_act_bwd_reduce(const float* grad_out, const float* out, float slope,
                                const float* y1, const float* mean1, const float* invstd1, double* red1,
                                const float* y2, const float* mean2, const float* invstd2, double* red2,
                                int64_t n, int32_t c, void* stream);
-/* Backward, pass 2 (train-mode BatchNorm): with xhat = (y - mean) * invstd,
+/* Backward of the same block, pass 2 (train-mode BatchNorm): with xhat = (y - mean) * invstd,
  *   grad_y = gamma*invstd * (g - red[0:c]/n - xhat * red[c:2c]/n),
  *   grad_gamma += red[c:2c], grad_beta += red[0:c]  (ACCUMULATED when the pointers are given: pass the parameters'
  *   .grad buffers, or zero-filled temporaries).
