@@ -247,7 +247,7 @@ int b200_affine_act_bwd_apply(const float* grad_out, const float* out, float slo
 
 /* ------------------------------------------------------- loss --------------------------
  * torch.nn.CrossEntropyLoss(weight | NULL, ignore_index, label_smoothing=0, reduction="mean") on [n, c] logits and
- * int64 targets (configs/model/criterion/*.yaml; models/model.py:117-118,135-136,152-153); c <= 32.
+ * int64 targets (configs/model/criterion/{CrossEntropyLoss,WeightedCrossEntropyLoss}.yaml; models/model.py:117-118,135-136,152-153); c <= 32.
  *   fwd: acc (fp64 [2]) and counter (uint32 [1]) are zero-filled scratch; loss_out fp32 [2] = {mean loss, sum of the
  *        weights of the rows that count} (the second value feeds the backward).  0 counted rows -> NaN like torch; a
  *        target outside [0, c) other than ignore_index also yields NaN (torch: device-side assert).

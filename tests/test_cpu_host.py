@@ -233,3 +233,26 @@ def test_scratch_arena_hands_out_zeroed_disjoint_slices():
     assert a.off == 0 and not a.buf.any()
     z = a.take(5, torch.float64)
     assert z.data_ptr() == x.data_ptr() and not z.any()
+
+
+def test_header_is_plain_c():
+    """include/b200randla.h is the drop-in boundary: it must compile as C99 (no C++-isms, no torch types) without
+    warnings, and link against the built library from a C translation unit."""
+    import pathlib
+    import subprocess
+    import tempfile
+
+    root = pathlib.Path(__file__).resolve().parents[1]
+    lib_dir = root / "myria3d_b200"
+    src = ('#include "b200randla.h"\n'
+           "int main(void) { return (b200_abi_version() == B200_ABI_VERSION && b200_last_error() != 0) ? 0 : 1; }\n")
+    with tempfile.TemporaryDirectory() as d:
+        c = pathlib.Path(d) / "t.c"
+        c.write_text(src)
+        subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-fsyntax-only",
+                        f"-I{root / 'include'}", str(c)], check=True)
+        exe = pathlib.Path(d) / "t"
+        r = subprocess.run(["gcc", "-std=c99", f"-I{root / 'include'}", str(c), "-o", str(exe), f"-L{lib_dir}",
+                            "-lb200randla", f"-Wl,-rpath,{lib_dir}"], capture_output=True, text=True)
+        if r.returncode == 0:  # linking needs the CUDA runtime the library depends on to be resolvable here
+            assert subprocess.run([str(exe)]).returncode == 0
