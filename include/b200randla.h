@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define B200_ABI_VERSION 3
+#define B200_ABI_VERSION 4
 
 #define B200_OK 0
 #define B200_E_INVALID 1     /* bad argument (null pointer, unsupported size/alignment) */
@@ -41,6 +41,15 @@ const char* b200_last_error(void);
 int64_t b200_launch_count(void);
 /* cudaGetDeviceProperties-based sanity check: 0 iff the current device is sm_100. */
 int b200_check_device(void);
+/* Process-wide switches (the library reads no environment variables).  Together with the launch counter these are
+ * the only mutable global state; compute entry points are otherwise pure functions of their arguments.
+ *   "tensor_cores"  1 (default) / 0: A/B switch that routes every tcgen05 kernel to its fp32-FMA counterpart
+ *                   (tests and profiles compare the two; no reference counterpart).
+ *   "tc_timeline"   device pointer (as integer) to 128 int64 receiving clock64() marks of CTA 0 of the tcgen05 GEMMs
+ *                   (scripts/tc_timeline.py); 0 (default) = off.
+ * b200_get_option returns the current value, -1 for an unknown key. */
+int b200_set_option(const char* key, int64_t value);
+int64_t b200_get_option(const char* key);
 
 /* ---------------------------------------------------------------- kNN ------------------
  * Replaces torch_cluster knn()/knn_graph() as called by
@@ -281,12 +290,16 @@ int b200_stitch_finalize(const float* reduced, const int64_t* idx, float* logits
                          float* entropy, int64_t m, int32_t c, void* stream);
 
 /* ------------------------------------------------------- tcgen05 self-test --------------
- * d[128, n] = a[128, k] * b[n, k]^T on the 5th-generation tensor cores (tcgen05.mma kind::tf32, TMEM
- * accumulator), with 1 (plain TF32) or 3 (3xTF32 split, fp32-grade) passes.  Pins the shared-memory
- * descriptor / TMEM conventions of the fused kernels.  *status (device int32): 0 = ok, 1 = the MMA
- * completion barrier timed out.  16 <= n <= 256, n % 16 == 0, k % 8 == 0. */
+ * d[128, n] (+)= a[128, k] * b[n, k]^T on the 5th-generation tensor cores (tcgen05.mma, TMEM accumulator):
+ * passes = 1 plain TF32, 3 = 3xTF32 split (kind::tf32), 6 = bf16 x 3 split (kind::f16, six cross products;
+ * the arithmetic of the fused LFA kernels); 3 and 6 are fp32-grade.  Pins the shared-memory descriptor / TMEM
+ * conventions of the fused kernels (no reference counterpart: test infrastructure of the kernels that replace
+ * pyg_randla_net.py:97-152).  flags: bit 0 / bit 1 = stage A / B transposed and read it through the MN-major
+ * descriptor (passes = 6 only); bit 2 = pre-initialise the accumulator from d with tcgen05.st and accumulate.
+ * *status (device int32): 0 = ok, 1 = the MMA completion barrier timed out.
+ * 16 <= n <= 256, n % 16 == 0, k % 8 == 0 (k % 16 == 0 for passes = 6). */
 int b200_tc_gemm_selftest(const float* a, const float* b, float* d, int32_t n, int32_t k, int32_t passes,
-                          int32_t* status, void* stream);
+                          int32_t flags, int32_t* status, void* stream);
 
 #ifdef __cplusplus
 }

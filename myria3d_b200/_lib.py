@@ -19,12 +19,14 @@ _SIGNATURES = {
     "b200_last_error": (c_char_p, []),
     "b200_launch_count": (c_int64, []),
     "b200_check_device": (c_int, []),
+    "b200_set_option": (c_int, [c_char_p, c_int64]),
+    "b200_get_option": (c_int64, [c_char_p]),
     "b200_knn": (c_int, [_P, _P, c_int64, _P, _P, c_int64, c_int32, c_int64, c_int32, c_int32, _P, _P, _P]),
     "b200_knn_grid_workspace_bytes": (c_int64, [c_int64, c_int32, c_int64]),
     "b200_knn_grid": (c_int, [_P, _P, c_int64, _P, _P, c_int64, c_int32, c_int64, c_int64, c_int32, c_int32, _P, _P, _P,
                               c_int64, _P]),
     "b200_adam_flat": (c_int, [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, _P, _P]),
-    "b200_tc_gemm_selftest": (c_int, [_P, _P, _P, c_int32, c_int32, c_int32, _P, _P]),
+    "b200_tc_gemm_selftest": (c_int, [_P, _P, _P, c_int32, c_int32, c_int32, c_int32, _P, _P]),
     "b200_edge_moments": (c_int, [_P, _P, c_int64, c_int32, _P, _P]),
     "b200_lfa_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int64, c_int32, c_int32, _P]),
     "b200_lfa_bwd_workspace_bytes": (c_int64, [c_int64, c_int32, c_int32]),
@@ -54,7 +56,7 @@ _SIGNATURES = {
     ),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 _lib = None
 

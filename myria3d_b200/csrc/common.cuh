@@ -44,9 +44,13 @@ size_t accumulate_at_b_workspace_bytes(int ca, int cb, int64_t n);
 int launch_tc_tn(const float* gy, int cout, const float* a1, int64_t ld1, int c1, const float* a2, int64_t ld2, int c2,
                  float* gw, float* gb, int64_t n, float* ws, size_t ws_bytes, cudaStream_t st);
 size_t tc_tn_workspace_bytes(int cout, int ncols, int64_t n);
-// fused LFA forward with the attention contraction on tcgen05 (lfa_tc.cu); B200_E_UNSUPPORTED -> use the FMA kernel
+// fused LFA forward / backward with every contraction on tcgen05 (lfa_tc.cu); B200_E_UNSUPPORTED -> use the FMA kernel
 int lfa_tc_fwd_dispatch(const float* x, const float* pos, const int32_t* nbr, const float* enc_w, const float* enc_b,
                         const float* att_wt, float* out, int64_t n, int c, int kt, cudaStream_t st);
+int lfa_tc_bwd_dispatch(const float* x, const float* pos, const int32_t* nbr, const float* enc_w, const float* enc_b,
+                        const float* att_w, const float* go, float* gx, float* gew, float* geb, float* gaw, int64_t n, int c,
+                        int kt, cudaStream_t st);
+bool lfa_tc_supported(int c, int kt);
 // row-streaming NT GEMM on tcgen05 (tc_nt.cu): out[i][m] = sum_k [a1|a2][i][k] * wm[m][k] + bias[m], channels of the
 // output split over two destination segments; colstats: fp64 (sum, sum of squares) per row tile [tiles][2 * mrows]
 bool tc_nt_shape_ok(int64_t n, int c1, int c2, int mrows);
@@ -55,7 +59,7 @@ int launch_tc_nt(const float* a1, int64_t ld1, int c1, const float* a2, int64_t 
                  const float* bias, float* o1, int64_t old1, int oc1, float* o2, int64_t old2, double* colstats, int64_t n,
                  cudaStream_t st);
 int launch_transpose(const float* w, float* wt, int rows, int cols, cudaStream_t st);
-bool tensor_cores_enabled();  // false iff B200_DISABLE_TCGEN05=1 (A/B switch for tests and profiles)
+bool tensor_cores_enabled();  // runtime.cu: b200_set_option("tensor_cores", 0) selects the FMA kernels (A/B switch)
 
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

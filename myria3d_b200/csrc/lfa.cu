@@ -20,8 +20,9 @@
 //            accumulators initialised with the direct term), x-gradients by vector red.global,
 //            encoder-gradient partials in shared memory, GEMM3 dW += da^T F as 4x4 register blocks.
 //
-// TODO(round 2): the three contractions run on the fp32 FMA pipe here; the tcgen05/TMEM version
-// maps channels to TMEM lanes and edges to columns so that the same thread-local softmax applies.
+// These FMA kernels serve c in {8, 16} (K = 8 / 16 contractions: 94 % of the edges, too narrow for a 128-lane
+// tensor tile) and c = 256; c in {32, 64, 128} run on tcgen05 (lfa_tc.cu), which maps channels to TMEM lanes and
+// edges to columns so that the same thread-local softmax applies.
 #include <math_constants.h>
 
 #include "common.cuh"
@@ -768,7 +769,7 @@ extern "C" int b200_lfa_fwd(const float* x, const float* pos, const int32_t* nbr
                "b200_lfa_fwd: x, att_wt and out must be 16-byte aligned");
   if (n <= 0) return B200_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  {  // c in {64, 128}: attention contraction on the tensor cores (lfa_tc.cu)
+  {  // c in {32, 64, 128}: every contraction on the tensor cores (lfa_tc.cu)
     const int rc = lfa_tc_fwd_dispatch(x, pos, nbr, enc_w, enc_b, att_wt, out, n, c, kt, st);
     if (rc != B200_E_UNSUPPORTED) return rc;
   }
@@ -781,7 +782,7 @@ extern "C" int b200_lfa_fwd(const float* x, const float* pos, const int32_t* nbr
 }
 
 extern "C" int64_t b200_lfa_bwd_workspace_bytes(int64_t n, int32_t c, int32_t kt) {
-  if (n <= 0 || c < 64) return 0;
+  if (n <= 0 || c < 64 || b200::lfa_tc_supported(c, kt)) return 0;  // tensor-core path: dW_att stays in TMEM
   return 2 * n * (int64_t)kt * c * (int64_t)sizeof(float) + (int64_t)b200::accumulate_at_b_workspace_bytes(c, c, n * kt);
 }
 
@@ -802,6 +803,11 @@ extern "C" int b200_lfa_bwd(const float* x, const float* pos, const int32_t* nbr
                B200_E_INVALID, "b200_lfa_bwd: workspace of %lld bytes needed (16-byte aligned)",
                (long long)b200_lfa_bwd_workspace_bytes(n, c, kt));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  {  // c in {32, 64, 128}: every contraction on the tensor cores (lfa_tc.cu)
+    const int rc = lfa_tc_bwd_dispatch(x, pos, nbr, enc_w, enc_b, att_w, grad_out, grad_x, grad_enc_w, grad_enc_b,
+                                       grad_att_w, n, c, kt, st);
+    if (rc != B200_E_UNSUPPORTED) return rc;
+  }
   float* ws = static_cast<float*>(workspace);
 #define X(C_, KT_, CW_, TC_, SPLIT_, ...)                                                                  \
   if (c == C_ && kt == KT_)                                                                                \

@@ -946,10 +946,6 @@ extern "C" int b200_linear_bwd_input(const float* grad_y, const float* w, float*
   return B200_OK;
 }
 
-namespace b200 { void set_tc_debug_buffer(long long* p); }
-// Debug hook (not part of the ABI header): device buffer of 128 int64 receiving clock64() marks of CTA 0.
-extern "C" void b200_debug_set_tc_timeline(long long* p) { b200::set_tc_debug_buffer(p); }
-
 extern "C" int64_t b200_linear_bwd_weight_workspace_bytes(int64_t n, int32_t c1, int32_t c2, int32_t cout, int32_t has_bias) {
   if (n <= 0 || cout < 64 || c1 + c2 < 64) return 0;
   return (int64_t)tc_tn_workspace_bytes(cout, c1 + c2 + (has_bias ? 1 : 0), n);

@@ -24,6 +24,12 @@ int cuda_fail(cudaError_t e, const char* what) {
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+// process-wide options (b200_set_option): the only mutable global state besides the launch counter
+static std::atomic<int> g_tensor_cores{1};
+static std::atomic<long long*> g_tc_timeline{nullptr};
+bool tensor_cores_enabled() { return g_tensor_cores.load(std::memory_order_relaxed) != 0; }
+long long* tc_debug_buffer() { return g_tc_timeline.load(std::memory_order_relaxed); }
+
 int num_sms() {
   static thread_local int cached_dev = -1;
   static thread_local int cached_sms = 148;
@@ -46,6 +52,27 @@ int b200_abi_version(void) { return B200_ABI_VERSION; }
 const char* b200_last_error(void) { return b200::g_err; }
 
 int64_t b200_launch_count(void) { return b200::g_launches.load(std::memory_order_relaxed); }
+
+int b200_set_option(const char* key, int64_t value) {
+  B200_REQUIRE(key, B200_E_INVALID, "b200_set_option: null key");
+  if (strcmp(key, "tensor_cores") == 0) {
+    b200::g_tensor_cores.store(value != 0, std::memory_order_relaxed);
+    return B200_OK;
+  }
+  if (strcmp(key, "tc_timeline") == 0) {
+    b200::g_tc_timeline.store(reinterpret_cast<long long*>(static_cast<intptr_t>(value)), std::memory_order_relaxed);
+    return B200_OK;
+  }
+  b200::set_error("b200_set_option: unknown option '%s' (known: tensor_cores, tc_timeline)", key);
+  return B200_E_INVALID;
+}
+
+int64_t b200_get_option(const char* key) {
+  if (key && strcmp(key, "tensor_cores") == 0) return b200::g_tensor_cores.load(std::memory_order_relaxed);
+  if (key && strcmp(key, "tc_timeline") == 0)
+    return static_cast<int64_t>(reinterpret_cast<intptr_t>(b200::g_tc_timeline.load(std::memory_order_relaxed)));
+  return -1;
+}
 
 int b200_check_device(void) {
   int dev = 0;

@@ -33,10 +33,57 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t smem_addr, uint32_t lbo, 
   return d;
 }
 
-// instruction descriptor: D fp32, A/B tf32, both K-major, dense
-__host__ __device__ constexpr uint32_t idesc_tf32(int m, int n) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+// instruction descriptor: D fp32, A/B tf32, dense.  a_mn / b_mn select the MN-major ("transposed") reading of
+// an operand (bits 15 / 16, cute::UMMA::InstrDescriptor::a_major_/b_major_).
+__host__ __device__ constexpr uint32_t idesc_tf32(int m, int n, bool a_mn = false, bool b_mn = false) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// 16-bit operands (kind::f16, bf16 x 3 split) and the MN-major ("transposed") reading of a buffer.
+//
+// tf32 operands can be read MN-major only from the SWIZZLE_128B_BASE32B layout (cutlass sm100_common.inl:
+// "for mn-major tf32 operands, SW128_32B is the only available smem layout"; a no-swizzle MN-major tf32 descriptor
+// multiplies by zero -- measured), so one tf32 buffer cannot serve both readings.  16-bit operands can: a plane
+//       uint16 smem[chunks][R+1][8]          (16-byte vector = 8 consecutive elements of the CHUNKED dimension)
+// is, without moving a byte,
+//   * K-major  (rows = M/N index, chunks along K):  ((8,n),2):((1,SBO),LBO) in 16-byte units with SBO = 8 (rows are
+//     contiguous), LBO = R+1 (chunk stride); one MMA (K = 16) reads 2 chunks; K += 16 adds 2 chunk strides;
+//   * MN-major (rows = K index, chunks along M/N):  ((1,n),(8,k)):((X,SBO),(1,LBO)) with LBO = 8 (the next group of
+//     8 K-rows follows directly), SBO = R+1 (stride between 8-wide M/N blocks); one MMA reads 16 rows; K += 16 adds
+//     256 bytes.  (cute::make_umma_desc<Major::MN>, LayoutType::INTERLEAVE.)
+// The fused LFA kernels (lfa_tc.cu) read W_att, F and dA both ways.
+__host__ __device__ constexpr size_t plane_halves(int rows, int chunked_dim) { return (size_t)(chunked_dim / 8) * (rows + 1) * 8; }
+// uint16 offset of element (row r, position c along the chunked dimension) inside a plane of `rows` rows
+__device__ __forceinline__ int plane_offset(int rows, int r, int c) { return ((c >> 3) * (rows + 1) + r) * 8 + (c & 7); }
+__device__ __forceinline__ uint64_t plane_desc_k(uint32_t plane_addr, int rows, int k0 /* multiple of 16 */) {
+  return smem_desc(plane_addr + (uint32_t)(k0 >> 3) * lbo_bytes(rows), lbo_bytes(rows), 128u);
+}
+__device__ __forceinline__ uint64_t plane_desc_mn(uint32_t plane_addr, int rows, int k0 /* row index, multiple of 16 */) {
+  return smem_desc(plane_addr + (uint32_t)k0 * 16u, /*lbo: next 8 K-rows*/ 128u, /*sbo: next 8-wide M/N block*/ lbo_bytes(rows));
+}
+// instruction descriptor: D fp32, A/B bf16, dense
+__host__ __device__ constexpr uint32_t idesc_bf16(int m, int n, bool a_mn = false, bool b_mn = false) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// bf16 x 3 split by truncation: v = t1 + t2 + t3 + r with |r| <= 2^-24 |v|; every t_i is exactly a bf16 (the high
+// half of an fp32 word), every residual is exact in fp32.  The six products t1t1', t1t2', t2t1', t2t2', t1t3', t3t1'
+// reproduce the fp32 product to ~2^-23 (dropped: t2t3', t3t2' ~ 2^-24, t3t3' ~ 2^-32).
+__device__ __forceinline__ void split_bf16x3(float v, uint32_t& t1, uint32_t& t2, uint32_t& t3) {
+  t1 = __float_as_uint(v) & 0xFFFF0000u;
+  const float r1 = v - __uint_as_float(t1);
+  t2 = __float_as_uint(r1) & 0xFFFF0000u;
+  const float r2 = r1 - __uint_as_float(t2);
+  t3 = __float_as_uint(r2) & 0xFFFF0000u;
+}
+// pack the bf16 (= high halves) of two fp32-word terms: low 16 bits <- a, high 16 bits <- b
+__device__ __forceinline__ uint32_t pack_hi16(uint32_t a, uint32_t b) { return __byte_perm(a, b, 0x7632); }
+// which term of A / B the p-th of the six passes multiplies
+__device__ __forceinline__ constexpr int bf16x3_term_a(int p) { return p == 2 || p == 3 ? 1 : (p == 5 ? 2 : 0); }
+__device__ __forceinline__ constexpr int bf16x3_term_b(int p) { return p == 1 || p == 3 ? 1 : (p == 4 ? 2 : 0); }
 
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_slot, uint32_t ncols) {  // one full warp
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "r"(ncols)
@@ -58,6 +105,16 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64
       ".reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"((uint32_t)accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
       "}" ::"r"(tmem_d),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"((uint32_t)accumulate)
       : "memory");
@@ -97,6 +154,18 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+
+// 16 consecutive fp32 columns of this thread's TMEM lane <- registers (accumulator pre-initialisation)
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+      "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+      "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+      "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // the same load without the wait: up to two of them in flight hide the TMEM read latency behind the previous block's
 // processing.  tmem_ld_wait takes the destination registers as in/out operands so that no use can be scheduled

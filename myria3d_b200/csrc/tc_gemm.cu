@@ -250,13 +250,6 @@ tc_tn_kernel(const float* __restrict__ gy, int cout, CatRowsTC A, float* __restr
 #undef B200_TS
 }
 
-bool tensor_cores_enabled() {
-  static const int enabled = [] {
-    const char* e = getenv("B200_DISABLE_TCGEN05");
-    return (e && e[0] == '1') ? 0 : 1;
-  }();
-  return enabled != 0;
-}
 
 // gw[m][c] += sum_s partial[s][m][c] (c < ktot), gb[m] += sum_s partial[s][m][ktot]
 __global__ void __launch_bounds__(256)
@@ -275,9 +268,7 @@ tc_reduce_partials_kernel(const float* __restrict__ partial, int splits, int cou
   }
 }
 
-static long long* g_tc_debug = nullptr;  // timeline buffer (128 x int64) for scripts/tc_timeline.py; never set in production
-void set_tc_debug_buffer(long long* p) { g_tc_debug = p; }
-long long* tc_debug_buffer() { return g_tc_debug; }
+long long* tc_debug_buffer();  // runtime.cu: b200_set_option("tc_timeline", ptr); null in production
 
 struct TcTnPlan {
   int bn;
@@ -318,7 +309,7 @@ static int launch_tc_tn_bn(const float* gy, int cout, const CatRowsTC& A, float*
   dim3 grid((unsigned)ceil_div(cout, 128), (unsigned)ceil_div(ncols, BN), (unsigned)p.splits);
   uint32_t cols = 32;
   while ((int)cols < BN) cols <<= 1;
-  kern<<<grid, TCG_THREADS, smem, st>>>(gy, cout, A, gw, gb, partial, n, p.rows_per_split, cols, g_tc_debug);
+  kern<<<grid, TCG_THREADS, smem, st>>>(gy, cout, A, gw, gb, partial, n, p.rows_per_split, cols, tc_debug_buffer());
   B200_CHECK_LAUNCH("tc_tn_kernel");
   if (partial) {
     int64_t blocks = ceil_div((int64_t)cout * ncols, 256);

@@ -13,15 +13,15 @@ y = torch.empty(n, cout, device=dev)
 parts = int(lib.b200_linear_fwd_num_stat_partials(n, k, 0, cout))
 stats = torch.empty(parts, 2 * cout, dtype=torch.float64, device=dev)
 dbg = torch.zeros(128, dtype=torch.int64, device=dev)
-lib.b200_debug_set_tc_timeline.argtypes = [c_void_p]
+lib.b200_set_option.argtypes = [ctypes.c_char_p, ctypes.c_int64]
 def run():
     _lib.check(lib.b200_linear_fwd(_p(a), k, k, None, 0, 0, _p(w), _p(b), _p(y), n, cout, _p(stats), _stream()), "x")
 for _ in range(3): run()
 torch.cuda.synchronize()
-lib.b200_debug_set_tc_timeline(c_void_p(dbg.data_ptr()))
+lib.b200_set_option(b"tc_timeline", dbg.data_ptr())
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record(); run(); e1.record(); torch.cuda.synchronize()
-lib.b200_debug_set_tc_timeline(None)
+lib.b200_set_option(b"tc_timeline", 0)
 t = dbg.cpu().tolist(); cnt = t[127]
 rel = [x - t[0] for x in t[:cnt]]
 nch = k // 32

@@ -11,17 +11,17 @@ dev = "cuda"
 a = torch.randn(n, c1, device=dev); gy = torch.randn(n, cout, device=dev)
 gw = torch.zeros(cout, c1, device=dev); gb = torch.zeros(cout, device=dev)
 dbg = torch.zeros(128, dtype=torch.int64, device=dev)
-lib.b200_debug_set_tc_timeline.argtypes = [c_void_p]
+lib.b200_set_option.argtypes = [ctypes.c_char_p, ctypes.c_int64]
 wsb = int(lib.b200_linear_bwd_weight_workspace_bytes(n, c1, 0, cout, 1))
 ws = torch.empty(max(wsb, 16), dtype=torch.uint8, device=dev)
 def run():
     _lib.check(lib.b200_linear_bwd_weight(_p(gy), _p(a), c1, c1, None, 0, 0, _p(gw), _p(gb), _p(ws), wsb, n, cout, _stream()), "x")
 for _ in range(3): run()
 torch.cuda.synchronize()
-lib.b200_debug_set_tc_timeline(c_void_p(dbg.data_ptr()))
+lib.b200_set_option(b"tc_timeline", dbg.data_ptr())
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record(); run(); e1.record(); torch.cuda.synchronize()
-lib.b200_debug_set_tc_timeline(None)
+lib.b200_set_option(b"tc_timeline", 0)
 t = dbg.cpu().tolist(); k = t[127]
 print(f"n={n} c1={c1} cout={cout}: kernel+reduce {e0.elapsed_time(e1)*1e3:.1f} us, {k} marks")
 base = t[0]

@@ -219,31 +219,70 @@ def test_lfa_module_parity(lib, c, k, training):
             assert_close(b, dict(ref.named_buffers())[name], atol=1e-5, rtol=1e-5, what=name)
 
 
-@pytest.mark.parametrize("c", [64, 128])
-def test_lfa_forward_tensor_core_path(lib, c, monkeypatch):
-    """The tcgen05 (3xTF32, TMEM) fused LFA forward (lfa_tc.cu, opt-in) gives the same pooled features as the FMA
-    kernel -- fp32-grade: rel 2e-5 -- on ragged clouds (degrees < K, partial last tile)."""
+@pytest.mark.parametrize("c,k", [(32, 16), (64, 16), (128, 16), (32, 32), (64, 32)])
+def test_lfa_tensor_core_path_vs_fma_and_fp64(lib, c, k):
+    """The tcgen05 (3xTF32, TMEM) fused LFA forward AND backward (lfa_tc.cu, the production path for c in
+    {32, 64, 128}) against (a) the fp32 FMA kernels of lfa.cu (`b200_set_option("tensor_cores", 0)`) and (b) an fp64
+    evaluation of pyg_randla_net.py:126-152 on the same folded encoder: pooled features, x-gradient, encoder and
+    attention-weight gradients, on ragged clouds (degrees < K, partial last tile).  fp32-grade: <= 1e-5 of the
+    tensor's scale against fp64."""
     from myria3d_b200 import ops
     from myria3d_b200.randla_net import _Level
 
-    sizes = [530, 9, 1, 77]
+    sizes = [530, 9, 1, 77, 2500]
     _, pos, _, ptr = rand_cloud(sizes, seed=c)
     n = sum(sizes)
     g = torch.Generator().manual_seed(c + 1)
-    x = torch.randn(n, c // 2, generator=g).to(DEV)
-    enc_w = (torch.randn(c // 2, 7, generator=g) * 0.5).to(DEV)
-    enc_b = (torch.randn(c // 2, generator=g) * 0.1).to(DEV)
-    att_w = (torch.randn(c, c, generator=g) / c ** 0.5).to(DEV)
+    x = torch.randn(n, c // 2, generator=g)
+    enc_w = torch.randn(c // 2, 7, generator=g) * 0.5
+    enc_b = torch.randn(c // 2, generator=g) * 0.1
+    att_w = torch.randn(c, c, generator=g) / c ** 0.5
+    go = torch.randn(n, c, generator=g)
     lvl = _Level(ptr.tolist(), torch.device(DEV))
     posd = pos.to(DEV)
-    nbr, _ = ops.knn(posd, lvl.ptr, posd, lvl.ptr, 16, lvl.max_n, kt=16, want_dist=False)
-    monkeypatch.delenv("B200_LFA_TCGEN05", raising=False)
-    ref = ops.lfa_attentive_pool(x, posd, nbr, enc_w, enc_b, att_w)
-    monkeypatch.setenv("B200_LFA_TCGEN05", "1")
-    out = ops.lfa_attentive_pool(x, posd, nbr, enc_w, enc_b, att_w)
-    torch.cuda.synchronize()
-    assert rel_err(out, ref) < 2e-5, rel_err(out, ref)
-    assert_close(out, ref, atol=2e-5 * float(ref.abs().max()), what="tcgen05 LFA forward")
+    kt = ops.table_width(k)
+    nbr, _ = ops.knn(posd, lvl.ptr, posd, lvl.ptr, k, lvl.max_n, kt=kt, want_dist=False)
+
+    def run():
+        leaves = [t.to(DEV).requires_grad_(True) for t in (x, enc_w, enc_b, att_w)]
+        out = ops.lfa_attentive_pool(leaves[0], posd, nbr, leaves[1], leaves[2], leaves[3])
+        out.backward(go.to(DEV))
+        torch.cuda.synchronize()
+        return [out.detach().cpu()] + [t.grad.cpu() for t in leaves]
+
+    assert lib.b200_get_option(b"tensor_cores") == 1
+    tc_res = run()
+    try:
+        assert lib.b200_set_option(b"tensor_cores", 0) == 0
+        fma_res = run()
+    finally:
+        lib.b200_set_option(b"tensor_cores", 1)
+
+    # fp64 ground truth (same formulation: q = (p_i, p_j, |p_j - p_i|), folded encoder, PyG softmax)
+    nb = nbr.cpu().long()
+    valid = nb >= 0
+    xd, wd, bd, ad = [t.double().requires_grad_(True) for t in (x, enc_w, enc_b, att_w)]
+    pi = pos.double()[:, None, :].expand(-1, kt, -1)
+    pj = pos.double()[nb.clamp(min=0)]
+    d = pj.float() - pi.float()
+    dist = torch.sqrt((d * d).sum(-1)).double()  # the kernels compute the distance in fp32 (reference order)
+    q = torch.cat([pi, pj, dist[..., None]], -1)
+    e = torch.nn.functional.leaky_relu(q @ wd.t() + bd, 0.2)
+    f = torch.cat([xd[nb.clamp(min=0)], e], -1) * valid[..., None]
+    a = f @ ad.t()
+    a = a.masked_fill(~valid[..., None], float("-inf"))
+    p = torch.exp(a - a.max(1, keepdim=True).values.detach())
+    s = p / (p.sum(1, keepdim=True) + 1e-16)
+    ref_out = (s * f).sum(1)
+    ref_out.backward(go.double())
+    ref = [ref_out.detach(), xd.grad, wd.grad, bd.grad, ad.grad]
+    names = ["out", "grad_x", "grad_enc_w", "grad_enc_b", "grad_att_w"]
+    for name, t, f_, r in zip(names, tc_res, fma_res, ref):
+        scale = float(r.abs().max())
+        err_tc = float((t.double() - r).abs().max()) / scale
+        err_fma = float((f_.double() - r).abs().max()) / scale
+        assert err_tc < 1e-5, f"{name}: tcgen05 path off by {err_tc:.2e} of scale (FMA path: {err_fma:.2e})"
+        assert err_fma < 1e-5, f"{name}: FMA path off by {err_fma:.2e} of scale"
 
 
 # ------------------------------------------------------------------------------ per-point layers
@@ -458,29 +497,35 @@ def test_knn_interpolate_bit_exact(lib, k, c):
 
 
 # ------------------------------------------------------------------------------ tcgen05 building blocks
-@pytest.mark.parametrize("n,k", [(128, 64), (64, 32), (256, 64), (16, 8), (128, 8)])
-def test_tcgen05_gemm_selftest(lib, n, k):
-    """tcgen05.mma kind::tf32 through our shared-memory descriptors + TMEM load path vs an fp64 product:
-    plain TF32 ~1e-3 relative, 3xTF32 ~1e-6 (fp32-grade)."""
+@pytest.mark.parametrize("flags", [0, 1, 2, 3, 4, 7])
+@pytest.mark.parametrize("n,k", [(128, 64), (64, 32), (256, 64), (16, 16), (128, 16), (32, 128)])
+def test_tcgen05_gemm_selftest(lib, n, k, flags):
+    """tcgen05.mma through our shared-memory descriptors + TMEM load/store path vs an fp64 product: plain TF32 ~1e-3
+    relative, 3xTF32 and bf16 x 3 (kind::f16, six cross products) ~1e-6 (fp32-grade).  flags bit 0/1: operand A/B
+    staged transposed and read through the MN-major descriptor (how the fused LFA backward re-reads dA, F and W_att in
+    place; 16-bit operands only); bit 2: the accumulator is pre-initialised with tcgen05.st."""
     from ctypes import c_void_p
 
     g = torch.Generator().manual_seed(n + k)
     a = torch.randn(128, k, generator=g)
     b = torch.randn(n, k, generator=g)
-    ref = (a.double() @ b.double().t())
+    d0 = torch.randn(128, n, generator=g) if flags & 4 else torch.zeros(128, n)
+    ref = (a.double() @ b.double().t()) + d0.double()
     scale = float(ref.abs().max())
     ad, bd = a.to(DEV), b.to(DEV)  # keep the device copies alive (the caching allocator would recycle temporaries)
-    for passes, tol in ((1, 3e-3), (3, 2e-6)):
-        d = torch.full((128, n), float("nan"), device=DEV)
+    for passes, tol in ((1, 3e-3), (3, 2e-6), (6, 2e-6)):
+        if passes != 6 and flags & 3:
+            continue  # tf32 operands have no no-swizzle MN-major reading (tc.cuh)
+        d = d0.to(DEV) if flags & 4 else torch.full((128, n), float("nan"), device=DEV)
         status = torch.zeros(1, dtype=torch.int32, device=DEV)
         rc = lib.b200_tc_gemm_selftest(c_void_p(ad.data_ptr()), c_void_p(bd.data_ptr()), c_void_p(d.data_ptr()),
-                                       n, k, passes, c_void_p(status.data_ptr()),
+                                       n, k, passes, flags, c_void_p(status.data_ptr()),
                                        c_void_p(torch.cuda.current_stream().cuda_stream))
         assert rc == 0, lib.b200_last_error()
         torch.cuda.synchronize()
         assert int(status) == 0, "tcgen05 completion barrier timed out"
         err = float((d.double().cpu() - ref).abs().max())
-        assert err <= tol * scale, f"passes={passes}: max err {err:.3e} vs scale {scale:.3e}"
+        assert err <= tol * scale, f"passes={passes} flags={flags}: max err {err:.3e} vs scale {scale:.3e}"
 
 
 # ------------------------------------------------------------------------------ loss
