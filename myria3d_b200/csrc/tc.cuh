@@ -54,6 +54,33 @@ __host__ __device__ constexpr uint32_t idesc_tf32(int m, int n, bool a_mn = fals
 //     8 K-rows follows directly), SBO = R+1 (stride between 8-wide M/N blocks); one MMA reads 16 rows; K += 16 adds
 //     256 bytes.  (cute::make_umma_desc<Major::MN>, LayoutType::INTERLEAVE.)
 // The fused LFA kernels (lfa_tc.cu) read W_att, F and dA both ways.
+// one lane of a converged warp (the tensor core instructions of a CTA are issued by a single thread; electing it
+// with elect.sync lets the compiler keep the descriptors in uniform registers without a per-instruction
+// uniformisation loop)
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+// descriptor of a plane with the start address left out: add (byte offset >> 4) to the low word per instruction
+__device__ __forceinline__ uint64_t plane_desc_k_base(uint32_t plane_addr, int rows) {
+  return smem_desc(plane_addr, lbo_bytes(rows), 128u);
+}
+__device__ __forceinline__ uint64_t plane_desc_mn_base(uint32_t plane_addr, int rows) {
+  return smem_desc(plane_addr, 128u, lbo_bytes(rows));
+}
+// advance a descriptor by a byte offset (multiple of 16; the 14-bit start-address field cannot overflow inside
+// the 227 KB of shared memory)
+__device__ __forceinline__ uint64_t desc_advance(uint64_t desc, uint32_t bytes) { return desc + (uint64_t)(bytes >> 4); }
+__host__ __device__ constexpr uint32_t plane_k_step_bytes(int rows) { return 2u * (uint32_t)(rows + 1) * 16u; }  // K += 16, K-major
+constexpr uint32_t kPlaneMnStepBytes = 256u;                                                                     // K += 16, MN-major
+
 __host__ __device__ constexpr size_t plane_halves(int rows, int chunked_dim) { return (size_t)(chunked_dim / 8) * (rows + 1) * 8; }
 // uint16 offset of element (row r, position c along the chunked dimension) inside a plane of `rows` rows
 __device__ __forceinline__ int plane_offset(int rows, int r, int c) { return ((c >> 3) * (rows + 1) + r) * 8 + (c & 7); }
@@ -119,6 +146,18 @@ __device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"((uint32_t)accumulate)
       : "memory");
 }
+// the same with the A operand in TENSOR MEMORY (lane = row of A, every 32-bit column = two consecutive K elements,
+// the even one in the low half): only B travels from shared memory
+__device__ __forceinline__ void mma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, bool accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"((uint32_t)accumulate)
+      : "memory");
+}
 // arrive on an mbarrier when all previously issued MMAs of this thread have completed
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -164,6 +203,28 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) 
       "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
       "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
       : "memory");
+}
+__device__ __forceinline__ void tmem_st16u(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+      "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+// one row of a bf16 x 3 A operand in tensor memory: 32 fp32 values (K = 32) -> 16 columns in each of the 3 planes
+// (plane t at column offset t * plane_cols from taddr)
+__device__ __forceinline__ void tmem_st_row32_bf16x3(uint32_t taddr, uint32_t plane_cols, const float (&v)[32]) {
+  uint32_t w[3][16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    uint32_t a1, a2, a3, b1, b2, b3;
+    split_bf16x3(v[2 * i], a1, a2, a3);
+    split_bf16x3(v[2 * i + 1], b1, b2, b3);
+    w[0][i] = pack_hi16(a1, b1), w[1][i] = pack_hi16(a2, b2), w[2][i] = pack_hi16(a3, b3);
+  }
+  tmem_st16u(taddr, w[0]);
+  tmem_st16u(taddr + plane_cols, w[1]);
+  tmem_st16u(taddr + 2 * plane_cols, w[2]);
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
