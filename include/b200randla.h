@@ -289,6 +289,19 @@ int b200_stitch_segment_sum(const float* rows, const int64_t* order, const int64
 int b200_stitch_finalize(const float* reduced, const int64_t* idx, float* logits, float* probas, int64_t* preds,
                          float* entropy, int64_t m, int32_t c, void* stream);
 
+/* ------------------------------------------------------- decimation draw ----------------
+ * Replaces decimation_indices() (myria3d/models/modules/pyg_randla_net.py:192-231): per cloud b, a uniformly random
+ * ORDERED subset of new_ptr[b+1] - new_ptr[b] of its ptr[b+1] - ptr[b] points (the distribution of
+ * ptr[b] + torch.randperm(n_b)[:n_b // decimation]), all clouds of the batch in one launch, no host sync.
+ * Random stream: Philox4x32-10 keyed by (seed, salt) and counted by (global point index, *counter); `counter`
+ * (device int64, may be NULL = 0) is read, never written: advance it with b200_counter_add between draws (both are
+ * CUDA-graph capturable).  idx_out[new_ptr[b] + t] (int64) receives the t-th drawn point of cloud b as an index into
+ * the batch.  max_kept = max_b (new_ptr[b+1] - new_ptr[b]) <= 25600 (B200_E_UNSUPPORTED beyond). */
+int b200_decimation_draw(const int64_t* ptr, const int64_t* new_ptr, int32_t num_clouds, int64_t max_kept, uint64_t seed,
+                         const int64_t* counter, uint32_t salt, int64_t* idx_out, void* stream);
+/* *counter += delta (single-thread kernel; device-side step / draw counters of captured graphs). */
+int b200_counter_add(int64_t* counter, int64_t delta, void* stream);
+
 /* ------------------------------------------------------- tcgen05 self-test --------------
  * d[128, n] (+)= a[128, k] * b[n, k]^T on the 5th-generation tensor cores (tcgen05.mma, TMEM accumulator):
  * passes = 1 plain TF32, 3 = 3xTF32 split (kind::tf32), 6 = bf16 x 3 split (kind::f16, six cross products;

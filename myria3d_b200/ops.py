@@ -302,6 +302,25 @@ class _GatherRows(torch.autograd.Function):
         return gx, None
 
 
+MAX_DRAW_KEPT = 25600  # b200_decimation_draw: kept points per cloud that fit its shared-memory sort
+
+
+def decimation_draw(ptr: Tensor, new_ptr: Tensor, max_kept: int, total_kept: int, seed: int, counter: Optional[Tensor],
+                    salt: int) -> Tensor:
+    """One launch for ``decimation_indices`` (pyg_randla_net.py:192-231): per cloud a uniformly random ordered
+    subset of ``new_ptr[b+1] - new_ptr[b]`` points, as int64 indices into the batch.  ``counter`` (device int64)
+    selects the draw; advance it with :func:`counter_add`."""
+    _need_cuda(ptr, new_ptr)
+    idx = torch.empty(total_kept, dtype=torch.int64, device=ptr.device)
+    _call("b200_decimation_draw", _p(ptr), _p(new_ptr), ptr.numel() - 1, max_kept, seed & 0xFFFFFFFFFFFFFFFF, _p(counter),
+          salt, _p(idx), _stream())
+    return idx
+
+
+def counter_add(counter: Tensor, delta: int = 1) -> None:
+    _call("b200_counter_add", _p(counter), delta, _stream())
+
+
 def gather_rows(x: Tensor, idx: Tensor) -> Tensor:
     _need_cuda(x, idx)
     if idx.dtype != torch.int64:

@@ -279,6 +279,8 @@ class B200RandLANet(nn.Module):
         # "reference": per-cloud torch.randperm calls exactly like pyg_randla_net.py:219-229 (same subsets as
         # the reference under a fixed seed on the same device); "fused": one batched draw per level.
         self.decimation_rng = "reference"
+        self._draw_counter: Optional[Tensor] = None  # device int64: index of the next fused draw
+        self._draw_seed = 0
         # parity harness hooks (never set in production)
         self.injected_decimation_idx: Optional[List[Tensor]] = None
         self.last_decimation_idx: List[Tensor] = []
@@ -301,8 +303,20 @@ class B200RandLANet(nn.Module):
         return levels
 
     def draw_decimation(self, levels: List["_Level"], lvl_idx: int) -> Tensor:
+        """``"fused"``: all clouds of the level in ONE kernel launch (``b200_decimation_draw``: Philox keys, radix select,
+        shared-memory sort; graph-capturable, the stream advances through a device counter); ``"reference"``: the
+        reference's per-cloud ``torch.randperm`` calls (same subsets as the reference under a fixed seed)."""
         if self.decimation_rng == "fused":
-            return fused_decimation_indices(levels[lvl_idx], levels[lvl_idx + 1].ptr_host)
+            lvl, nxt = levels[lvl_idx], levels[lvl_idx + 1]
+            if nxt.max_n > ops.MAX_DRAW_KEPT:  # > 102 400 points per cloud: batched torch draw (random keys + sort)
+                return fused_decimation_indices(lvl, nxt.ptr_host)
+            if self._draw_counter is None or self._draw_counter.device != lvl.ptr.device:
+                self._draw_counter = torch.zeros(1, dtype=torch.int64, device=lvl.ptr.device)
+                self._draw_seed = int(torch.initial_seed())
+            idx = ops.decimation_draw(lvl.ptr, nxt.ptr, nxt.max_n, nxt.n, self._draw_seed, self._draw_counter, lvl_idx)
+            if lvl_idx == 3:  # the last draw of a forward pass: the next pass gets fresh permutations
+                ops.counter_add(self._draw_counter, 1)
+            return idx
         return decimation_indices(levels[lvl_idx].ptr_host, self.decimation, levels[lvl_idx].ptr.device)[0]
 
     def _decimate(self, tensors, levels: List["_Level"], lvl_idx: int):

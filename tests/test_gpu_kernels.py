@@ -497,6 +497,54 @@ def test_knn_interpolate_bit_exact(lib, k, c):
     assert_close(xg.grad, xr.grad, atol=1e-5, rtol=1e-5, what="interp grad")
 
 
+# ------------------------------------------------------------------------------ decimation draw
+def test_decimation_draw_kernel(lib):
+    """b200_decimation_draw == the distribution of ``ptr[b] + torch.randperm(n_b)[:max(1, n_b // 4)]``
+    (pyg_randla_net.py:216-221): valid (distinct, in-cloud, right counts), deterministic in (seed, counter, salt),
+    fresh per counter value, and uniform: chi-square of the inclusion counts and of the FIRST drawn position."""
+    from myria3d_b200 import ops
+    from myria3d_b200.randla_net import decimation_sizes
+
+    sizes = [12800, 1, 3, 50, 4097, 65536]
+    ptr_h = ptr_of(sizes)
+    new_h = decimation_sizes(ptr_h, 4)
+    ptr, new_ptr = torch.tensor(ptr_h, device=DEV), torch.tensor(new_h, device=DEV)
+    kept = [new_h[i + 1] - new_h[i] for i in range(len(sizes))]
+    counter = torch.zeros(1, dtype=torch.int64, device=DEV)
+    idx = ops.decimation_draw(ptr, new_ptr, max(kept), new_h[-1], 1234, counter, 2).cpu()
+    for b, (n, k) in enumerate(zip(sizes, kept)):
+        part = idx[new_h[b]:new_h[b + 1]]
+        assert k == max(1, n // 4) and part.numel() == k
+        assert int(part.min()) >= ptr_h[b] and int(part.max()) < ptr_h[b + 1]
+        assert part.unique().numel() == k, "duplicates in the draw"
+    again = ops.decimation_draw(ptr, new_ptr, max(kept), new_h[-1], 1234, counter, 2).cpu()
+    assert torch.equal(idx, again), "not a function of (seed, counter, salt)"
+    other_salt = ops.decimation_draw(ptr, new_ptr, max(kept), new_h[-1], 1234, counter, 3).cpu()
+    assert not torch.equal(idx, other_salt)
+    ops.counter_add(counter, 1)
+    fresh = ops.decimation_draw(ptr, new_ptr, max(kept), new_h[-1], 1234, counter, 2).cpu()
+    assert int(counter) == 1 and not torch.equal(idx, fresh)
+    assert not torch.equal(idx[:3200].sort().values, fresh[:3200].sort().values), "same subset twice"
+
+    # uniformity on a small cloud: 64 points, 16 kept, 4000 draws
+    ptr2, new2 = torch.tensor([0, 64], device=DEV), torch.tensor([0, 16], device=DEV)
+    trials = 4000
+    incl = torch.zeros(64)
+    first = torch.zeros(64)
+    pair_order = 0
+    for t in range(trials):
+        d = ops.decimation_draw(ptr2, new2, 16, 16, 99, counter, 0).cpu()
+        ops.counter_add(counter, 1)
+        incl[d] += 1
+        first[d[0]] += 1
+        pair_order += int(d[0] < d[1])
+    exp_incl, exp_first = trials * 16 / 64, trials / 64
+    chi_incl = float(((incl - exp_incl) ** 2 / (exp_incl * (1 - 16 / 64))).sum())  # ~ chi2(63)
+    chi_first = float(((first - exp_first) ** 2 / exp_first).sum())              # ~ chi2(63)
+    assert chi_incl < 120 and chi_first < 120, (chi_incl, chi_first)              # p ~ 1e-5 at 63 dof
+    assert abs(pair_order / trials - 0.5) < 0.04, "the order inside the subset is not random"
+
+
 # ------------------------------------------------------------------------------ tcgen05 building blocks
 @pytest.mark.parametrize("flags", [0, 1, 2, 3, 4, 7, 8, 14])
 @pytest.mark.parametrize("n,k", [(128, 64), (64, 32), (256, 64), (16, 16), (128, 16), (32, 128)])
