@@ -300,6 +300,141 @@ knn_grid_kernel(const float4* __restrict__ sorted, const int* __restrict__ start
   }
 }
 
+// ---- 5b. warp-cooperative ring search (production path for the kNN graph: kt = 16 or 32 neighbour slots)
+// A group of LANES = kt lanes (half a warp for K = 16) serves one query.  The group keeps the current top-k as a
+// sorted list DISTRIBUTED over its lanes (lane l holds the l-th best (distance, index) pair); candidates are read LANES
+// at a time with one coalesced load per group, filtered against the k-th best pair with a ballot, and every survivor
+// is inserted with one ballot + two shuffles (rank = number of list entries sorting before it; the lanes behind shift up
+// by one).  This is the "warp-shuffle top-k": no data-dependent per-thread insertion loop, every lane does useful work
+// in every instruction (round 1's thread-per-query kernel ran 7.6 of 32 lanes).  All loops have warp-uniform trip
+// counts (ring rows by offset, batches by the longer of the two groups' runs), so the two half-warp groups of a warp --
+// in cell order they usually sit in the same cell -- never diverge and full-mask shuffles are legal throughout.
+// Ordering is the same lexicographic (distance, index) rule as everywhere else: results are bit-identical to knn.cu.
+template <int LANES, bool SELF>
+__global__ void __launch_bounds__(GRID_THREADS)
+knn_grid_warp_kernel(const float4* __restrict__ sorted, const int* __restrict__ starts, const GridMeta* __restrict__ meta,
+                     const int64_t* __restrict__ ptr_x, const float* __restrict__ pos_y, const int64_t* __restrict__ ptr_y,
+                     int stride, int k, int kt, int32_t* __restrict__ nbr, float* __restrict__ dist2) {
+  constexpr int QPW = 32 / LANES, QPB = (GRID_THREADS / 32) * QPW;
+  constexpr unsigned FULL = 0xffffffffu;
+  constexpr unsigned GMASK = (LANES == 32) ? 0xffffffffu : ((1u << (LANES & 31)) - 1u);
+  const int cloud = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lg = lane % LANES, gshift = (lane / LANES) * LANES;
+  const int64_t xs = ptr_x[cloud], xe = ptr_x[cloud + 1];
+  const int64_t ys = SELF ? xs : ptr_y[cloud], ye = SELF ? xe : ptr_y[cloud + 1];
+  const int64_t t = ys + (int64_t)blockIdx.x * QPB + warp * QPW + lane / LANES;
+  const bool active = t < ye;  // group-uniform
+  if (!__any_sync(FULL, active)) return;
+
+  float q0 = 0.f, q1 = 0.f, q2 = 0.f;
+  int64_t out_row = 0;
+  if (active) {
+    if (SELF) {
+      const float4 s = sorted[t];  // t-th point of the cloud in cell order
+      q0 = s.x, q1 = s.y, q2 = s.z;
+      out_row = __float_as_int(s.w);
+    } else {
+      q0 = pos_y[3 * t], q1 = pos_y[3 * t + 1], q2 = pos_y[3 * t + 2];
+      out_row = t;
+    }
+  }
+  float d = CUDART_INF_F;  // this lane's entry of the group's sorted top list
+  int id = -1;
+
+  if (xe > xs) {
+    const GridMeta m = meta[cloud];
+    const int g = m.g;
+    const int* st = starts + (int64_t)cloud * (stride + 1);
+    const float4* pts = sorted + xs;
+    const float qa = (m.da == 0) ? q0 : ((m.da == 1) ? q1 : q2);
+    const float qb = (m.db == 0) ? q0 : ((m.db == 1) ? q1 : q2);
+    const int ca = grid_cell_1d(qa, m.oa, m.inva, g), cb = grid_cell_1d(qb, m.ob, m.invb, g);
+    bool done = !active;
+
+    for (int r = 0;; ++r) {
+      const int a0 = ca - r, a1 = ca + r, b0 = cb - r, b1 = cb + r;
+      const int alo = a0 < 0 ? 0 : a0, ahi = a1 > g - 1 ? g - 1 : a1;
+      for (int db = -r; db <= r; ++db) {
+        const int bb = cb + db;
+        const bool row_ok = !done && bb >= 0 && bb <= g - 1;
+        const bool full_row = (db == -r || db == r);
+        // run 1 = the whole ring row (contiguous in the sorted array) or the left cell of an interior row,
+        // run 2 = the right cell of an interior row
+        int s1 = 0, e1 = 0, s2 = 0, e2 = 0;
+        if (row_ok) {
+          const int* row = st + bb * g;
+          if (full_row) {
+            s1 = row[alo], e1 = row[ahi + 1];
+          } else {
+            if (a0 >= 0) s1 = row[a0], e1 = row[a0 + 1];
+            if (a1 <= g - 1) s2 = row[a1], e2 = row[a1 + 1];
+          }
+        }
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+          const int s = pass ? s2 : s1, e = pass ? e2 : e1;
+          int len = e - s;
+          if (LANES < 32) len = max(len, __shfl_xor_sync(FULL, len, 16));  // the longer of the two groups' runs
+          for (int u0 = 0; u0 < len; u0 += LANES) {
+            const int u = s + u0 + lg;
+            const bool valid = u < e;
+            float dc = CUDART_INF_F;
+            int ic = 0x7fffffff;
+            if (valid) {
+              const float4 c = __ldg(pts + u);
+              dc = dist2_rn(c.x, c.y, c.z, q0, q1, q2);
+              ic = __float_as_int(c.w);
+            }
+            const float kd = __shfl_sync(FULL, d, k - 1, LANES);
+            const int ki = __shfl_sync(FULL, id, k - 1, LANES);
+            const bool passes = valid && (dc < kd || (dc == kd && (ki < 0 || ic < ki)));
+            unsigned mm = (__ballot_sync(FULL, passes) >> gshift) & GMASK;
+            while (__any_sync(FULL, mm != 0)) {
+              const bool has = mm != 0;
+              const int src = has ? (__ffs(mm) - 1) : 0;
+              mm &= mm - 1;
+              const float bd = __shfl_sync(FULL, dc, src, LANES);
+              const int bi = __shfl_sync(FULL, ic, src, LANES);
+              // rank of the candidate = list entries sorting before it (empty slots: distance +inf, never before)
+              const bool before = (d < bd) || (d == bd && id >= 0 && id < bi);
+              const int pos = __popc((__ballot_sync(FULL, before) >> gshift) & GMASK);
+              const float pd = __shfl_up_sync(FULL, d, 1, LANES);
+              const int pi = __shfl_up_sync(FULL, id, 1, LANES);
+              if (has && pos < k) {
+                if (lg > pos) {
+                  d = pd, id = pi;
+                } else if (lg == pos) {
+                  d = bd, id = bi;
+                }
+              }
+            }
+          }
+        }
+      }
+      if (a0 <= 0 && a1 >= g - 1 && b0 <= 0 && b1 >= g - 1) done = true;  // the whole grid has been visited
+      const float kth = __shfl_sync(FULL, d, k - 1, LANES);  // (outside the branch: both groups execute it together)
+      if (!done && kth < CUDART_INF_F) {
+        // every unvisited point lies outside the block [a0, a1] x [b0, b1]: lower-bound its distance
+        float mind = CUDART_INF_F;
+        if (a0 > 0) mind = fminf(mind, qa - (m.oa + (float)a0 * m.wa));
+        if (a1 < g - 1) mind = fminf(mind, (m.oa + (float)(a1 + 1) * m.wa) - qa);
+        if (b0 > 0) mind = fminf(mind, qb - (m.ob + (float)b0 * m.wb));
+        if (b1 < g - 1) mind = fminf(mind, (m.ob + (float)(b1 + 1) * m.wb) - qb);
+        mind -= m.slack;
+        if (mind > 0.f && mind * mind > kth) done = true;
+      }
+      if (__all_sync(FULL, done)) break;
+    }
+  }
+
+  if (active && lg < kt) {
+    const bool keep = (lg < k) && (id >= 0);
+    nbr[out_row * kt + lg] = keep ? id : -1;
+    if (dist2) dist2[out_row * kt + lg] = keep ? d : CUDART_INF_F;
+  }
+}
+
 struct GridWorkspace {
   GridMeta* meta;
   int* counts;
@@ -383,6 +518,19 @@ extern "C" int b200_knn_grid(const float* pos_x, const int64_t* ptr_x, int64_t n
   } else {
     grid_scan_kernel<<<(unsigned)num_clouds, 256, 0, st>>>(ptr_x, w.counts, w.starts, stride);
     B200_CHECK_LAUNCH("grid_scan_kernel");
+  }
+  if ((kt == 16 || kt == 32) && k > 1) {  // kNN graph / k = 10 interpolation: warp-cooperative search
+    const int qpb = (GRID_THREADS / 32) * (32 / kt);
+    dim3 grid((unsigned)ceil_div(max_y_per_cloud, qpb), (unsigned)num_clouds);
+#define B200_WARP_CASE(L, S) \
+    knn_grid_warp_kernel<L, S><<<grid, GRID_THREADS, 0, st>>>(w.sorted, w.starts, w.meta, ptr_x, pos_y, ptr_y, stride, k, kt, nbr, dist2)
+    if (kt == 16 && self) B200_WARP_CASE(16, true);
+    else if (kt == 16) B200_WARP_CASE(16, false);
+    else if (self) B200_WARP_CASE(32, true);
+    else B200_WARP_CASE(32, false);
+#undef B200_WARP_CASE
+    B200_CHECK_LAUNCH("knn_grid_warp_kernel");
+    return B200_OK;
   }
 #define B200_KNN_CASE(KM) \
   if (k <= KM) return launch_grid_search<KM>(self, w, ptr_x, pos_y, ptr_y, stride, num_clouds, max_y_per_cloud, k, kt, nbr, dist2, st)

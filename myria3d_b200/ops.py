@@ -124,7 +124,7 @@ def table_width(k: int) -> int:
 
 
 # ------------------------------------------------------------------------------------------- kNN
-GRID_KNN_MIN_POINTS = 1024  # clouds at least this large use the bucket-grid search (measured crossover)
+GRID_KNN_MIN_POINTS = 512  # kNN graph (kt = 16/32): measured crossover ~400 points per cloud (grid 60 us vs brute 92 us at 800)
 
 
 def knn(pos_x: Tensor, ptr_x: Tensor, pos_y: Tensor, ptr_y: Tensor, k: int, max_queries_per_cloud: int,
@@ -154,7 +154,9 @@ def knn(pos_x: Tensor, ptr_x: Tensor, pos_y: Tensor, ptr_y: Tensor, k: int, max_
     nbr = torch.empty((ny, kt), dtype=torch.int32, device=pos_y.device)
     dist2 = torch.empty((ny, kt), dtype=torch.float32, device=pos_y.device) if want_dist else None
     if algo == "auto":
-        algo = "grid" if max_x >= GRID_KNN_MIN_POINTS else "brute"
+        # the warp-cooperative grid search serves neighbour tables (kt = 16 / 32); the thread-per-query grid kernel
+        # behind k = 1 interpolation queries only pays off on larger clouds
+        algo = "grid" if max_x >= (GRID_KNN_MIN_POINTS if kt in (16, 32) and k > 1 else 1024) else "brute"
     if algo == "grid":
         nbytes = int(_lib.load().b200_knn_grid_workspace_bytes(nx, num_clouds, max_x))
         ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=pos_x.device)
