@@ -271,9 +271,10 @@ int b200_cross_entropy_bwd(const float* logits, const int64_t* target, const flo
  * One Adam update over FLAT fp32 buffers (parameters, gradients, first and second moments), the arithmetic of
  * torch.optim.Adam(lr, betas, eps) without weight decay / amsgrad (configs/model/optimizer/Adam.yaml uses the
  * defaults).  *step (device int64) is incremented first and used for the bias corrections, so the call is
- * CUDA-graph capturable.  All buffers 16-byte aligned. */
-int b200_adam_flat(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
-                   float lr, float beta1, float beta2, float eps, int64_t* step, void* stream);
+ * CUDA-graph capturable.  lr_dev (device float, may be NULL) overrides lr: a captured graph then follows a
+ * learning-rate scheduler (configs/model/lr_scheduler/).  All buffers 16-byte aligned. */
+int b200_adam_flat(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                   const float* lr_dev, float beta1, float beta2, float eps, int64_t* step, void* stream);
 
 /* ------------------------------------------------------- sliding-window stitch ---
  * b200_stitch_segment_sum replaces torch_scatter.scatter_sum(logits, idx_in_full_cloud, out=zeros(nb_points, C))

@@ -25,7 +25,7 @@ _SIGNATURES = {
     "b200_knn_grid_workspace_bytes": (c_int64, [c_int64, c_int32, c_int64]),
     "b200_knn_grid": (c_int, [_P, _P, c_int64, _P, _P, c_int64, c_int32, c_int64, c_int64, c_int32, c_int32, _P, _P, _P,
                               c_int64, _P]),
-    "b200_adam_flat": (c_int, [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, _P, _P]),
+    "b200_adam_flat": (c_int, [_P, _P, _P, _P, c_int64, c_float, _P, c_float, c_float, c_float, _P, _P]),
     "b200_decimation_draw": (c_int, [_P, _P, c_int32, c_int64, ctypes.c_uint64, _P, ctypes.c_uint32, _P, _P]),
     "b200_counter_add": (c_int, [_P, c_int64, _P]),
     "b200_tc_gemm_selftest": (c_int, [_P, _P, _P, c_int32, c_int32, c_int32, c_int32, _P, _P]),

@@ -10,7 +10,9 @@ namespace b200 {
 
 __global__ void __launch_bounds__(256)
 adam_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                 int64_t n, float lr, float b1, float b2, float eps, const int64_t* __restrict__ step) {
+                 int64_t n, float lr_host, const float* __restrict__ lr_dev, float b1, float b2, float eps,
+                 const int64_t* __restrict__ step) {
+  const float lr = lr_dev ? *lr_dev : lr_host;  // device scalar: a captured graph follows the lr scheduler
   const double t = (double)(*step);
   const float bc1 = (float)(1.0 - pow((double)b1, t));
   const float bc2_sqrt = (float)sqrt(1.0 - pow((double)b2, t));
@@ -47,7 +49,7 @@ __global__ void increment_kernel(int64_t* step) { *step += 1; }
 using namespace b200;
 
 extern "C" int b200_adam_flat(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
-                              float beta1, float beta2, float eps, int64_t* step, void* stream) {
+                              const float* lr_dev, float beta1, float beta2, float eps, int64_t* step, void* stream) {
   B200_REQUIRE(params && grads && exp_avg && exp_avg_sq && step, B200_E_INVALID, "b200_adam_flat: null pointer");
   B200_REQUIRE((((uintptr_t)params | (uintptr_t)grads | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) == 0, B200_E_INVALID,
                "b200_adam_flat: buffers must be 16-byte aligned");
@@ -57,7 +59,7 @@ extern "C" int b200_adam_flat(float* params, const float* grads, float* exp_avg,
   B200_CHECK_LAUNCH("increment_kernel");
   int64_t blocks = ceil_div(n / 4 + 1, 256);
   if (blocks > (int64_t)num_sms() * 4) blocks = (int64_t)num_sms() * 4;
-  adam_flat_kernel<<<(unsigned)blocks, 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, step);
+  adam_flat_kernel<<<(unsigned)blocks, 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, n, lr, lr_dev, beta1, beta2, eps, step);
   B200_CHECK_LAUNCH("adam_flat_kernel");
   return B200_OK;
 }

@@ -6,14 +6,22 @@ consecutive batches share their layout (same ``ptr``: e.g. myria3d tiles subsamp
 budget, BASELINE configs[1]), the whole step -- gradient zeroing, forward, CrossEntropyLoss, backward and
 the optimizer update -- is captured once and replayed.
 
-Randomness stays outside the capture: the decimation subsets (``decimation_indices``,
-pyg_randla_net.py:192-231) are drawn eagerly -- by default with one batched draw per level
-(``fused_decimation_indices``), optionally with the reference's per-cloud ``torch.randperm`` stream -- and
-handed to the graph through static index buffers; dropout uses torch's graph-safe Philox state.  One graph is
-kept per batch layout.
+Randomness: by default the decimation subsets (``decimation_indices``, pyg_randla_net.py:192-231) are drawn INSIDE
+the graph by ``b200_decimation_draw`` (one kernel per level, device-side draw counter); optionally the reference's
+per-cloud ``torch.randperm`` stream is drawn eagerly and handed to the graph through static index buffers.  Dropout
+uses torch's graph-safe Philox state.
+
+Training semantics are those of the eager loop: capturing a new layout (warm-up passes + capture) runs on a
+snapshot of the parameters, optimizer state, BatchNorm buffers and draw counter which is restored before the first
+replay, so the batch that triggers a capture is trained exactly once.  At most ``max_graphs`` layouts are kept
+(least recently used evicted); a layout is captured only after it has been seen ``capture_after`` times, until then
+(and for anything that cannot be captured) the step runs eagerly -- with myria3d's variable point budget most batches
+are one-off layouts and simply take the eager path.  Layouts are identified by the HOST copy of ``ptr`` (a CPU
+``batch.ptr`` or ``batch.ptr_host``); a device-only ``ptr`` is read back every step (one small sync).
 """
 from __future__ import annotations
 
+from collections import OrderedDict
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -46,8 +54,12 @@ class GraphedTrainStep:
     all-reduce runs between the captured forward/backward graph and the captured optimizer graph.
     """
 
-    def __init__(self, model, optimizer, reducer=None, warmup_steps: int = 3, decimation_rng: str = "fused"):
+    def __init__(self, model, optimizer, reducer=None, warmup_steps: int = 3, decimation_rng: str = "fused",
+                 max_graphs: int = 8, capture_after: int = 0):
         self.model = model
+        self.max_graphs = max(1, int(max_graphs))
+        self.capture_after = max(0, int(capture_after))
+        self._seen: Dict[Tuple[int, ...], int] = {}
         self.net = model.model
         self.optimizer = optimizer
         self.reducer = reducer
@@ -55,8 +67,7 @@ class GraphedTrainStep:
         # "fused" (default): one batched draw per level; "reference": the reference's per-cloud randperm stream
         self.net.decimation_rng = decimation_rng
         self.device = next(model.parameters()).device
-        self._captured: Dict[Tuple[int, ...], _Captured] = {}
-        self._key_cache: Dict[Tuple[int, int], Tuple[int, ...]] = {}
+        self._captured: "OrderedDict[Tuple[int, ...], _Captured]" = OrderedDict()
         self.library_launches = 0  # kernels of libb200randla replayed so far
 
     # ------------------------------------------------------------------ helpers
@@ -76,10 +87,50 @@ class GraphedTrainStep:
         out["loss"].backward()
         return out
 
-    def _capture(self, batch) -> _Captured:
+    def _state_tensors(self) -> List[Tensor]:
+        """Everything a training step mutates: parameters, optimizer state, module buffers (BatchNorm running
+        statistics / counters), the fused-draw counter."""
+        ts: List[Tensor] = [p.data for p in self.model.parameters()] + list(self.model.buffers())
+        for attr in ("flat_params", "exp_avg", "exp_avg_sq", "step_count"):
+            t = getattr(self.optimizer, attr, None)
+            if isinstance(t, Tensor):
+                ts.append(t)
+        for st in self.optimizer.state.values():
+            ts.extend(v for v in st.values() if isinstance(v, Tensor))
+        if getattr(self.net, "_draw_counter", None) is not None:
+            ts.append(self.net._draw_counter)
+        seen, out = set(), []
+        for t in ts:  # parameters of FlatAdam are views of flat_params: keep one copy per storage range
+            k = (t.data_ptr(), t.numel(), t.dtype)
+            if k not in seen:
+                seen.add(k)
+                out.append(t)
+        return out
+
+    def _capture(self, batch, key=None) -> _Captured:
+        """Warm-up + capture on a snapshot of the training state (restored in place afterwards)."""
+        tensors = self._state_tensors()
+        if getattr(self.net, "_draw_counter", None) is None and self.net.decimation_rng == "fused":
+            self.net.draw_decimation(self.net.levels_for([int(v) for v in (key or batch.ptr.tolist())], self.device), 0)
+            tensors = self._state_tensors()  # the draw counter exists now
+        snap = [(t, t.clone()) for t in tensors]
+        known = {(t.data_ptr(), t.numel(), t.dtype) for t in tensors}
+        try:
+            cap = self._capture_impl(batch, key)
+        finally:
+            with torch.no_grad():
+                for t, s0 in snap:
+                    t.copy_(s0)
+                # optimizer state created lazily by the warm-up steps (torch.optim.Adam): back to its initial zeros
+                for t in self._state_tensors():
+                    if (t.data_ptr(), t.numel(), t.dtype) not in known:
+                        t.zero_()
+        return cap
+
+    def _capture_impl(self, batch, key=None) -> _Captured:
         cap = _Captured()
         dev = self.device
-        cap.ptr_host = [int(v) for v in batch.ptr.tolist()]
+        cap.ptr_host = [int(v) for v in (key if key is not None else batch.ptr.tolist())]
         for k in ("x", "pos", "y", "batch", "ptr"):
             cap.static[k] = getattr(batch, k).to(dev, non_blocking=True).clone()
         levels = self.net.levels_for(cap.ptr_host, dev)
@@ -126,24 +177,54 @@ class GraphedTrainStep:
             self.net.static_ptr_host, self.net.injected_decimation_idx = prev_static, prev_inj
         return cap
 
-    def _layout_key(self, ptr: Tensor) -> Tuple[int, ...]:
-        """``tuple(ptr)``; device tensors are read back once per (storage, version) to avoid a sync per step."""
+    @staticmethod
+    def _layout_key(batch) -> Tuple[int, ...]:
+        """``tuple(ptr)`` from the HOST: a CPU ``batch.ptr``, else ``batch.ptr_host``; a device-only ``ptr`` costs one
+        small device->host read per step (a storage address is not an identity: the caching allocator recycles it)."""
+        ptr = batch.ptr
         if not ptr.is_cuda:
             return tuple(int(v) for v in ptr.tolist())
-        ck = (ptr.data_ptr(), ptr._version)
-        key = self._key_cache.get(ck)
-        if key is None:
-            if len(self._key_cache) > 64:
-                self._key_cache.clear()
-            key = self._key_cache[ck] = tuple(int(v) for v in ptr.tolist())
-        return key
+        if "ptr_host" in batch:
+            return tuple(int(v) for v in batch.ptr_host)
+        return tuple(int(v) for v in ptr.tolist())
+
+    def _eager_step(self, batch) -> Tensor:
+        """The same step without a graph (one-off layouts)."""
+        if hasattr(self.optimizer, "sync_lr"):
+            self.optimizer.sync_lr()
+        self._zero_grad()
+        b = batch.to(self.device, non_blocking=True) if not batch.pos.is_cuda else batch
+        out = self.model.training_step(b, 0)
+        out["loss"].backward()
+        if self.reducer is not None:
+            self.reducer.all_reduce()
+        self.optimizer.step()
+        self._last_eager = {"loss": out["loss"].detach(), "logits": out["logits"].detach(), "targets": b.y}
+        return self._last_eager["loss"]
 
     # ------------------------------------------------------------------ call
     def __call__(self, batch) -> Tensor:
-        key = self._layout_key(batch.ptr)
+        key = self._layout_key(batch)
+        multi = self.reducer is not None and self.reducer.world_size > 1
+        if multi:
+            self.reducer.broadcast_buffers()  # torch DDP's broadcast_buffers=True (rank 0's BatchNorm statistics)
         cap = self._captured.get(key)
         if cap is None:
-            cap = self._captured[key] = self._capture(batch)
+            n_seen = self._seen.get(key, 0)
+            if n_seen < self.capture_after:
+                if len(self._seen) > 4096:
+                    self._seen.clear()
+                self._seen[key] = n_seen + 1
+                self._last_key = None
+                return self._eager_step(batch)
+            while len(self._captured) >= self.max_graphs:  # least recently used layout goes (frees its memory pool)
+                self._captured.popitem(last=False)
+            cap = self._captured[key] = self._capture(batch, key)
+        else:
+            self._captured.move_to_end(key)
+        self._last_key = key
+        if hasattr(self.optimizer, "sync_lr"):
+            self.optimizer.sync_lr()
         for k in ("x", "pos", "y", "batch"):
             cap.static[k].copy_(getattr(batch, k), non_blocking=True)
         if not cap.draws_in_graph:
@@ -162,5 +243,7 @@ class GraphedTrainStep:
         return cap.loss
 
     def last_outputs(self, batch) -> Dict[str, Tensor]:
-        cap = self._captured[self._layout_key(batch.ptr)]
+        cap = self._captured.get(self._layout_key(batch))
+        if cap is None or getattr(self, "_last_key", None) is None:
+            return dict(self._last_eager)
         return {"loss": cap.loss, "logits": cap.logits, "targets": cap.static["y"]}

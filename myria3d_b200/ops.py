@@ -43,14 +43,36 @@ def _call(name: str, *args) -> None:
     prof.add(name, args, start, end)
 
 
+# Storages (untyped_storage().data_ptr()) whose owners asked for direct gradient accumulation: the flat gradient
+# buffers of FlatGradAllReducer (and so of FlatAdam / GraphedTrainStep, which are built on it).
+_DIRECT_GRAD_STORAGES: set = set()
+
+
+def enable_direct_grads(flat: Tensor) -> None:
+    """Allow the backward kernels to accumulate parameter gradients straight into views of ``flat``."""
+    _DIRECT_GRAD_STORAGES.add(flat.untyped_storage().data_ptr())
+
+
+def disable_direct_grads(flat: Tensor) -> None:
+    _DIRECT_GRAD_STORAGES.discard(flat.untyped_storage().data_ptr())
+
+
 def _direct_grad(p: Optional[Tensor]) -> Optional[Tensor]:
-    """``p.grad`` when a backward kernel may accumulate straight into it (it exists, is a dense fp32 buffer such
-    as a view of FlatGradAllReducer's flat buffer, and nothing hooks the parameter), else None.  Saves the
-    zero-fill of a temporary and autograd's AccumulateGrad add per parameter; the result (p.grad += g) is the same."""
-    if p is None or not isinstance(p, torch.nn.Parameter) or not p.requires_grad:
+    """``p.grad`` when a backward kernel may accumulate straight into it, else None (the gradient then goes back
+    through autograd's AccumulateGrad node like any other op's).
+
+    Direct accumulation is OPT-IN: only gradients that are views of a buffer registered with
+    :func:`enable_direct_grads` qualify -- the flat buffer of :class:`myria3d_b200.parallel.FlatGradAllReducer`, whose
+    owner reduces it itself.  Anything that relies on AccumulateGrad running (torch DDP's reducer hooks it, so do
+    ``register_post_accumulate_grad_hook`` users) therefore keeps working: with plain ``p.grad`` tensors this function
+    returns None.  Saves the zero-fill of a temporary and the AccumulateGrad add per parameter; the result
+    (p.grad += g) is the same."""
+    if not _DIRECT_GRAD_STORAGES or p is None or not isinstance(p, torch.nn.Parameter) or not p.requires_grad:
         return None
     g = p.grad
     if g is None or g.dtype != torch.float32 or not g.is_contiguous() or g.shape != p.shape or not g.is_cuda:
+        return None
+    if g.untyped_storage().data_ptr() not in _DIRECT_GRAD_STORAGES:
         return None
     if p._backward_hooks or getattr(p, "_post_accumulate_grad_hooks", None):
         return None

@@ -42,6 +42,14 @@ class FlatGradAllReducer:
             n = p.numel()
             p.grad = self.flat[offset:offset + n].view_as(p)
             offset += n
+        # the backward kernels may accumulate straight into these views (ops._direct_grad): this class, not
+        # autograd hooks, is what reduces them
+        from . import ops
+
+        ops.enable_direct_grads(self.flat)
+        self._buffers: Optional[List[torch.Tensor]] = None
+        self._flat_buffers: Optional[torch.Tensor] = None
+        self._module = module
 
     @property
     def world_size(self) -> int:
@@ -63,6 +71,26 @@ class FlatGradAllReducer:
 
     def zero_grad(self) -> None:
         self.flat.zero_()
+
+    def broadcast_buffers(self, src: int = 0) -> None:
+        """torch DDP's default ``broadcast_buffers=True``: before every forward, rank ``src``'s floating buffers (the
+        BatchNorm running statistics: 8 179 floats) replace everybody else's, so that every rank checkpoints the
+        same state (the reference trains with Lightning's stock DDP,
+        configs/experiment/RandLaNet_base_run_FR-MultiGPU.yaml:9-13).  One flat broadcast per call; a no-op on one
+        rank.  ``num_batches_tracked`` counters advance identically on every rank and are left alone."""
+        if self.world_size == 1:
+            return
+        if self._buffers is None:
+            self._buffers = [b for b in self._module.buffers() if b.is_floating_point()]
+            self._flat_buffers = torch.empty(sum(b.numel() for b in self._buffers), dtype=torch.float32,
+                                             device=self.flat.device)
+        if not self._buffers:
+            return
+        torch._foreach_copy_(list(self._flat_buffers.split([b.numel() for b in self._buffers])),
+                             [b.reshape(-1) for b in self._buffers])
+        dist.broadcast(self._flat_buffers, src=src, group=self.group)
+        torch._foreach_copy_([b.reshape(-1) for b in self._buffers],
+                             list(self._flat_buffers.split([b.numel() for b in self._buffers])))
 
 
 def shard_tiles(num_tiles: int, rank: int, world_size: int) -> List[int]:

@@ -256,3 +256,26 @@ def test_header_is_plain_c():
                             "-lb200randla", f"-Wl,-rpath,{lib_dir}"], capture_output=True, text=True)
         if r.returncode == 0:  # linking needs the CUDA runtime the library depends on to be resolvable here
             assert subprocess.run([str(exe)]).returncode == 0
+
+
+def test_checkpoint_unpickler_does_not_resolve_code_globals(tmp_path):
+    """the stub unpickler whitelists tensor-rebuilding helpers and plain containers only; a pickle that
+    names builtins.eval / os.system gets inert stubs (nothing is executed) while tensors still load."""
+    import pickle
+
+    from myria3d_b200.ckpt import _StubUnpickler, load_lightning_checkpoint
+
+    class Evil:
+        def __reduce__(self):
+            return (eval, ("__import__('os').system('echo pwned > %s')" % (tmp_path / "pwned"),))
+
+    import io
+
+    blob = pickle.dumps({"x": Evil(), "n": 3})
+    out = _StubUnpickler(io.BytesIO(blob)).load()
+    assert out["n"] == 3 and not (tmp_path / "pwned").exists()
+    path = tmp_path / "c.ckpt"
+    torch.save({"state_dict": {"model.fc0.weight": torch.ones(2, 3)}, "evil": Evil(), "epoch": 1}, path)
+    ck = load_lightning_checkpoint(str(path))
+    assert torch.equal(ck["state_dict"]["model.fc0.weight"], torch.ones(2, 3)) and ck["epoch"] == 1
+    assert not (tmp_path / "pwned").exists()
