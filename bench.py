@@ -56,7 +56,20 @@ def parse_args():
     ap.add_argument("--decimation-rng", choices=["fused", "reference"], default="fused",
                     help="fused: one batched random draw per level; reference: per-cloud torch.randperm like the reference")
     ap.add_argument("--kernel-report", default=None, help="write the per-kernel table (JSON) here")
-    return ap.parse_args()
+    ap.add_argument("--config", choices=["B", "D", "E"], default="B",
+                    help="BASELINE.json workload: B = configs[1]/[2] (default: 16 x 12 800-pt tiles, K=16, train step); "
+                         "E = configs[4] (4 x 65 536-pt tiles per GPU, K=32, train step); D = configs[3] (inference-only "
+                         "predict path: 50 x 40 960-pt tiles per batch, k=10 interpolation to the 60 000-pt windows, stitch)")
+    args = ap.parse_args()
+    global K_NEIGHBORS
+    if args.config == "E":
+        K_NEIGHBORS = 32
+        args.tiles, args.points = 4, 65536
+        args.cpu_tiles, args.cpu_steps = 1, 2
+    elif args.config == "D":
+        args.tiles, args.points = 50, 40960
+        args.cpu_tiles, args.cpu_steps = 1, 2
+    return args
 
 
 def peaks():
@@ -286,9 +299,13 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    res = cpu_reference(args.cpu_tiles, args.points, args.steps, max(args.warmup, 1))
+    if args.config == "D":
+        res = cpu_reference_predict(args.cpu_tiles, args.points, min(args.steps, 3), 1)
+    else:
+        res = cpu_reference(args.cpu_tiles, args.points, args.steps if args.config == "B" else min(args.steps, 3),
+                            max(args.warmup, 1) if args.config == "B" else 1)
     line = {
-        "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "impl": "reference", "metric": METRIC if args.config != "D" else "points/sec (predict path) RandLA-Net 40960-pt tiles", "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, 1, "reference"),
@@ -296,13 +313,18 @@ def run_reference(args):
         "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if args.config == "D":
+        line["config"]["step"] = ("inference only, reference CPU path: eval forward + k=10 interpolation + stitch on a bounded "
+                                  f"sample of {args.cpu_tiles} window(s) per step; value counts FULL-cloud points")
+        line["config"]["points_per_step"] = args.cpu_tiles * FULL_POINTS
     print(json.dumps(line), flush=True)
 
 
 def workload_config(args, world, impl="b200"):
+    which = {"B": "configs[1]" + ("/[2]" if world > 1 else ""), "E": "configs[4]", "D": "configs[3]"}[args.config]
     return {
         "workload": f"RandLA-Net full (4 down/4 up), K={K_NEIGHBORS}, {args.points} pts/tile, batch={args.tiles}/GPU "
-                    f"(BASELINE configs[1]{'/[2]' if world > 1 else ''})",
+                    f"(BASELINE {which})",
         "optimizer": ("torch.optim.Adam (CPU)" if impl == "reference" else
                       "torch.optim.Adam(fused)" if getattr(args, "torch_adam", False) else "FlatAdam (b200_adam_flat)"),
         "step": "fwd + CrossEntropyLoss + bwd + flat NCCL grad all-reduce (N>1) + Adam; "
@@ -315,6 +337,180 @@ def workload_config(args, world, impl="b200"):
                                            "4 rotating input batches",
     }
 
+
+
+# ------------------------------------------------------------------------------ config D: predict path
+FULL_POINTS = 60000   # points of a 50 m window before the 40 960-point budget (docs/source/background/general_design.md:42)
+WINDOW_STRIDE = 45000  # consecutive windows share 15 000 points of the stitched cloud (sliding-window overlap)
+CLASSES = {1: "unclassified", 2: "ground", 6: "building", 9: "water", 17: "bridge", 64: "lasting_above"}
+
+
+def predict_batch(tiles: int, sub: int, seed: int, first_point: int = 0):
+    """Host batch of `tiles` receptive fields as myria3d's predict dataloader yields them: the sub-sampled cloud the
+    network sees, `copies` with the full-resolution positions, `idx_in_original_cloud` for the stitch."""
+    import numpy as np
+
+    from myria3d_b200 import Batch, Data
+    from myria3d_b200.synthetic import synthetic_tile
+
+    g = torch.Generator().manual_seed(seed)
+    datas = []
+    for w in range(tiles):
+        x, pos, y = synthetic_tile(FULL_POINTS, seed=seed + w, num_features=NUM_FEATURES, num_classes=NUM_CLASSES)
+        keep = torch.randperm(FULL_POINTS, generator=g)[:sub]
+        d = Data(x=x[keep], pos=pos[keep], y=y[keep])
+        d.copies = {"pos_copy": pos, "pos_sampled_copy": pos[keep]}
+        lo = first_point + w * WINDOW_STRIDE
+        d.idx_in_original_cloud = np.arange(lo, lo + FULL_POINTS, dtype=np.int64)
+        datas.append(d)
+    return Batch.from_data_list(datas), first_point + WINDOW_STRIDE * (tiles - 1) + FULL_POINTS
+
+
+def cpu_reference_predict(tiles: int, sub: int, steps: int, warmup: int):
+    """The reference's CPU predict path (oracle port): eval forward, k=10 interpolation to the full window
+    (models/model.py:86-98), scatter-sum stitch + softmax + argmax + entropy (models/interpolation.py:98-166)."""
+    from oracle import randla_oracle as O
+
+    torch.manual_seed(12345)
+    torch.set_num_threads(min(os.cpu_count() or 1, 16))
+    net = O.OracleRandLANet(NUM_FEATURES, NUM_CLASSES, decimation=DECIMATION, num_neighbors=K_NEIGHBORS, return_logits=True).eval()
+    batch, nb = predict_batch(tiles, sub, 12345)
+    ptr_y = [0]
+    for a in batch.idx_in_original_cloud:
+        ptr_y.append(ptr_y[-1] + len(a))
+    idx = torch.cat([torch.from_numpy(a) for a in batch.idx_in_original_cloud])
+
+    def step():
+        with torch.no_grad():
+            logits = net(batch.x, batch.pos, batch.batch, batch.ptr)
+            full = O.knn_interpolate(logits, batch.copies["pos_sampled_copy"], batch.copies["pos_copy"],
+                                     [int(v) for v in batch.ptr], ptr_y, 10)
+            red = torch.zeros(nb, NUM_CLASSES).index_add_(0, idx, full)
+            probas = red[idx].softmax(1)
+            return probas.argmax(1), torch.distributions.Categorical(probs=probas).entropy()
+
+    for _ in range(max(warmup, 1)):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return {"value": tiles * FULL_POINTS / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{tiles} windows of {FULL_POINTS} pts ({sub} after sub-sampling) per step, {warmup} warm-up + {steps} "
+                      "timed steps, oracle eval forward + kd-tree k=10 interpolation + torch scatter stitch",
+            "ms_per_step": dt * 1e3}
+
+
+def run_b200_predict(args):
+    """BASELINE configs[3]: inference only.  A step = one predict batch: eval forward on `tiles` receptive fields of
+    `points` points, k=10 interpolation of the logits to every point of the 60 000-point windows, sliding-window stitch.
+    Multi-GPU = independent replicas on different tiles (no collective on the data path)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import datetime
+
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
+    from myria3d_b200 import Model, _lib, ops
+    from myria3d_b200.build import build_library
+    from myria3d_b200.interpolation import Interpolator
+
+    if rank == 0:
+        build_library()
+    if world > 1:
+        dist.barrier()
+    _lib.check(_lib.load().b200_check_device(), "b200_check_device")
+    torch.manual_seed(12345)
+    model = Model(neural_net_class_name="B200RandLANet",
+                  neural_net_hparams=dict(num_features=NUM_FEATURES, num_classes=NUM_CLASSES, num_neighbors=K_NEIGHBORS,
+                                          decimation=DECIMATION, return_logits=True),
+                  criterion=torch.nn.CrossEntropyLoss(ignore_index=65), interpolation_k=10, num_workers=1).to(dev).eval()
+    model.model.decimation_rng = "fused"
+    n_rot = 2
+    host, nb_points = [], 0
+    for r in range(n_rot):
+        b, nb_points = predict_batch(args.tiles, args.points, 5000 + 1000 * rank + 100 * r)
+        host.append(b.pin_memory())
+    resident = [b.to(dev) for b in host]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    h2d = sum(t.numel() * t.element_size() for t in (host[0].x, host[0].pos, host[0].batch, host[0].ptr,
+                                                     host[0].copies["pos_copy"], host[0].copies["pos_sampled_copy"]))
+    out_host = torch.empty(args.tiles * FULL_POINTS, dtype=torch.int64).pin_memory()
+
+    def step(batch):
+        with torch.no_grad():
+            _, logits = model.forward(batch)  # network + k=10 interpolation on the GPU (SURVEY 8f-1)
+            itp = Interpolator(interpolation_k=10, classification_dict=CLASSES)
+            itp.store_predictions(logits, batch.idx_in_original_cloud)
+            reduced, idx, _ = itp._reduce(nb_points)
+            return ops.stitch_finalize(reduced, idx, want_logits=False)  # probas, preds, entropy per prediction
+
+    def timed(kind, steps):
+        evs = []
+        for s in range(steps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            if kind == "resident":
+                step(resident[s % n_rot])
+            else:
+                res = step(host[s % n_rot].to(dev, non_blocking=True))
+                out_host.copy_(res[2], non_blocking=True)  # predicted classes of the batch's points back to the host
+                torch.cuda.current_stream().synchronize()
+            e1.record()
+            evs.append((e0, e1))
+        torch.cuda.synchronize()
+        return sum(a.elapsed_time(b) for a, b in evs)
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for s in range(max(args.warmup, 3)):
+        step(resident[s % n_rot])
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = _lib.launch_count()
+    total_ms = max_over_ranks(timed("resident", args.steps))
+    launches = (_lib.launch_count() - l0) // max(args.steps, 1)
+    if world > 1:
+        dist.barrier()
+    e2e_ms = max_over_ranks(timed("e2e", args.steps))
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        pts = args.tiles * FULL_POINTS
+        ms = total_ms / args.steps
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            res = cpu_reference_predict(args.cpu_tiles, args.points, args.cpu_steps, 1)
+            cpu = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        cfg = workload_config(args, world)
+        cfg["step"] = ("inference only: eval forward + k=10 interpolation of the logits to the 60 000-point windows + "
+                       "sliding-window stitch (scatter-sum, softmax, argmax, entropy); value counts FULL-cloud points")
+        cfg["points_per_step"] = pts * world
+        line = {"metric": "points/sec (predict path) RandLA-Net 40960-pt tiles", "value": pts * world / (ms * 1e-3), "unit": UNIT,
+                "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg, "clocks": clocks,
+                "gpu_launches": int(launches),
+                "e2e": {"value": pts * world / (e2e_ms / args.steps * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                        "d2h_bytes_per_step": int(out_host.numel() * 8), "ms_per_step": e2e_ms / args.steps},
+                "roofline": None, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 # ------------------------------------------------------------------------------ B200 arm
 def run_b200(args):
@@ -511,6 +707,8 @@ def main():
     args = parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.config == "D":
+        run_b200_predict(args)
     else:
         run_b200(args)
 

@@ -37,6 +37,13 @@ class Data:
         return int(self.pos.shape[0])
 
     def to(self, device, non_blocking: bool = False):
+        """Move every tensor (also inside ``copies``).  The host copy of ``ptr`` travels along as ``ptr_host`` (a
+        tuple): consumers that need the batch layout on the host (``GraphedTrainStep``, ``B200RandLANet`` with
+        ``static_ptr_host``) then never read the device ``ptr`` back."""
+        store = self.__dict__["_store"]
+        if "ptr_host" not in store and isinstance(store.get("ptr"), Tensor) and not store["ptr"].is_cuda:
+            store["ptr_host"] = tuple(int(v) for v in store["ptr"].tolist())
+
         def move(v):
             if isinstance(v, Tensor):
                 return v.to(device, non_blocking=non_blocking)

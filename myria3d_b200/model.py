@@ -19,7 +19,7 @@ import torch
 from torch import nn
 
 from . import ops
-from .randla_net import B200RandLANet
+from .randla_net import B200Block1Net, B200RandLANet
 
 try:  # pragma: no cover - depends on the environment
     from pytorch_lightning import LightningModule as _Base
@@ -36,7 +36,7 @@ except Exception:  # Lightning absent: minimal shim
             pass
 
 
-MODEL_ZOO = [B200RandLANet]
+MODEL_ZOO = [B200RandLANet, B200Block1Net]  # the full net first: "RandLANet" keeps resolving to it
 
 
 def get_neural_net_class(class_name: str) -> nn.Module:

@@ -376,3 +376,32 @@ class B200RandLANet(nn.Module):
         if self.return_logits:
             return logits
         return logits.log_softmax(dim=-1)  # :87
+
+
+class B200Block1Net(nn.Module):
+    """``fc0 + block1 + head`` -- the "1 encoder layer" network of BASELINE.json configs[0] (SURVEY.md section 8d,
+    config A), the reference's CPU-runnable case: no decimation, no decoder.  Same sub-module names as
+    :class:`B200RandLANet` (``fc0``, ``block1``, ``mlp_classif``, ``fc_classif``: a full state dict loads with
+    ``strict=False``), same kernels, same ``forward(x, pos, batch, ptr)`` signature."""
+
+    def __init__(self, num_features: int, num_classes: int, num_neighbors: int = 16, return_logits: bool = True):
+        super().__init__()
+        ops.table_width(num_neighbors)
+        d_bottleneck = max(32, num_classes, num_features)  # pyg_randla_net.py:40
+        self.fc0 = nn.Linear(num_features, d_bottleneck)
+        self.block1 = DilatedResidualBlock(num_neighbors, d_bottleneck, 32)
+        self.mlp_classif = SharedMLP([32, 64, 32], dropout=[0.0, 0.5])
+        self.fc_classif = nn.Linear(32, num_classes)
+        self.return_logits = return_logits
+
+    def forward(self, x: Optional[Tensor], pos: Tensor, batch: Optional[Tensor], ptr: Tensor) -> Tensor:
+        if not pos.is_cuda:
+            raise RuntimeError("B200Block1Net runs on a CUDA (B200) device only; there is no CPU fallback")
+        x = x if x is not None else pos
+        pos = pos.float().contiguous()
+        ops.reset_scratch(pos.device)
+        lvl0 = _Level([int(v) for v in ptr.tolist()], pos.device)
+        h0 = ops.linear(x, self.fc0.weight, self.fc0.bias)
+        b1 = self.block1(h0, pos, lvl0)
+        logits = ops.linear(self.mlp_classif(b1), self.fc_classif.weight, self.fc_classif.bias)
+        return logits if self.return_logits else logits.log_softmax(dim=-1)

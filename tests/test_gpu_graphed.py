@@ -128,7 +128,11 @@ def test_capture_trains_the_first_batch_exactly_once(lib):
             # noise into +-lr steps in either implementation.  ONE step of at most lr each: |difference| <= 2 lr
             assert float((p1 - p2).abs().max()) <= 2.01 * 2e-3, n1
             continue
-        assert torch.allclose(p1, p2, atol=2e-6, rtol=1e-5), (n1, float((p1 - p2).abs().max()))
+        # first Adam step = lr * g / (|g| + eps): +-lr wherever |g| >> eps, noise-sensitive only for ~1e-8 gradients.
+        # A second training pass on this batch would move every weight by another ~lr = 2e-3
+        # (an element whose gradient is fp32 noise around zero may step the other way in the two runs: <= 2 lr apart)
+        d = (p1 - p2).abs().flatten()
+        assert float(d.max()) <= 2.01 * 2e-3 and float(d.float().quantile(0.99)) <= 5e-5, (n1, float(d.max()), float(d.median()))
     for (n1, b1), (_, b2) in zip(m.named_buffers(), ref.named_buffers()):
         assert torch.allclose(b1.float(), b2.float(), atol=1e-6, rtol=1e-5), n1  # num_batches_tracked == 1, running stats
 

@@ -76,15 +76,14 @@ def _run_train_parity(sizes, k=16, num_classes=6, seed=0, check_grads=True):
     print(f"sizes {sizes}: fp32-oracle noise {noise:.2e}, tolerance {tol:.2e}")
     assert_close(logits, logits64, atol=tol, what=f"train logits {sizes}")
     assert abs(float(loss) - float(loss64)) < max(1e-4, 10 * abs(float(loss_ref) - float(loss64)))
-    if noise > 1e-4:
-        # ill-conditioned batch (2-row BatchNorms): gradients are noise-dominated in ANY fp32 implementation,
-        # the fp32 oracle itself is off by percents; only require finite gradients of the right shape
-        for name, p in net.named_parameters():
-            assert p.grad is not None and torch.isfinite(p.grad).all(), name
-        check_grads = False
+    # (ill-conditioned batches -- 2-row BatchNorms in the reference's [50, 50] case -- are NOT exempt from the gradient
+    # check: every parameter gradient must be within max(1e-3, 10 x the fp32 oracle's own error) of the fp64 gradient)
     if check_grads:
         g64 = {k_: p.grad for k_, p in ref64.named_parameters()}
         g32 = {k_: p.grad for k_, p in ref.named_parameters()}
+        # yardstick for an ill-conditioned batch: the WORST error the fp32 oracle (= the reference's own arithmetic)
+        # makes on any parameter gradient of this batch (round-off amplification is chaotic per parameter)
+        e32_worst = max(rel_err(g32[k_], g64[k_]) for k_ in g64 if float(g64[k_].abs().max()) > 1e-6)
         worst = ("", 0.0)
         for name, p in net.named_parameters():
             assert p.grad is not None, f"no grad for {name}"
@@ -99,7 +98,8 @@ def _run_train_parity(sizes, k=16, num_classes=6, seed=0, check_grads=True):
             if e > worst[1] and not small:
                 worst = (name, e)
             # rel 1e-3 on every parameter gradient, relaxed like the logits when ill-conditioned
-            assert e < max(1e-3, 10 * e32) or small, f"grad {name}: rel err {e:.3e} (fp32 oracle: {e32:.3e})"
+            assert e < max(1e-3, 10 * e32, 10 * e32_worst if noise > 1e-4 else 0.0) or small, \
+                f"grad {name}: rel err {e:.3e} (fp32 oracle: {e32:.3e}, its worst parameter: {e32_worst:.3e})"
         print("worst grad rel err", worst)
     ref_bufs = dict(ref64.named_buffers())
     for name, b in net.named_buffers():
@@ -114,6 +114,15 @@ def test_train_step_parity(lib, sizes):
 
 def test_train_step_parity_k32(lib):
     _run_train_parity([900, 40], k=32)
+
+
+def test_train_step_parity_baseline_tile(lib):
+    """Train-mode NUMERICAL parity at the BASELINE tile size (the reference's own test only checks shapes at
+    [12500, 12500], tests/myria3d/models/modules/test_randla_nets.py:8-40): one 12 800-point tile + a 3 000-point one.
+    Exercises what the small cases cannot: the tcgen05 GEMMs with their BatchNorm-statistics epilogue (n >= 1024 rows
+    at >= 64 channels), the warp-cooperative grid kNN on levels 0-1, the tensor-core LFA forward / backward with many
+    tiles per slot and the periodic dW flush.  Ground truth: the fp64 oracle."""
+    _run_train_parity([12800, 3000], seed=3)
 
 
 @pytest.mark.parametrize("num_nodes", [[12500, 12500], [50, 50], [12500, 10000]])
@@ -194,8 +203,15 @@ def test_checkpoint_state_dict_and_model_wrapper(lib):
     batch.idx_in_original_cloud = [torch.arange(2000).numpy(), torch.arange(900).numpy()]
     with torch.no_grad():
         targets, logits_full = model(batch.to(DEV))
-        _, logits_sub = model.model(batch.x.to(DEV), batch.pos.to(DEV), None, batch.ptr.to(DEV)), None
     assert targets is None and logits_full.shape == (2900, 7)
+    # the GPU interpolation (b200_knn k = 10 + b200_knn_interp) == PyG knn_interpolate(k = interpolation_k) of
+    # model.py:90-98 applied to the same sub-sampled logits, cloud by cloud
+    model.model.injected_decimation_idx = [t.clone() for t in model.model.last_decimation_idx]  # eval decimates too
+    with torch.no_grad():
+        logits_sub = model.model(batch.x.to(DEV), batch.pos.to(DEV), None, batch.ptr.to(DEV)).cpu()
+    model.model.injected_decimation_idx = None
+    expect = O.knn_interpolate(logits_sub, torch.cat(sub), torch.cat(full), [0, 600, 900], [0, 2000, 2900], 10, method="brute")
+    assert_close(logits_full, expect, atol=2e-5 * float(expect.abs().max()), what="eval logits interpolated to the full cloud")
     pred = model.predict_step(batch.to(DEV))
     assert pred["logits"].device.type == "cpu" and pred["logits"].shape == (2900, 7)
 
@@ -288,3 +304,45 @@ def test_against_trained_checkpoint_golden(lib):
     assert_close(logits, g["logits_fp64"], atol=tol, what="eval logits vs trained-checkpoint golden (fp64 oracle)")
     agree = (logits.argmax(1).cpu() == g["logits_fp64"].argmax(1)).float().mean()
     assert float(agree) >= 0.999, float(agree)
+
+
+def test_config_a_block1_net_parity(lib):
+    """BASELINE.json configs[0] ('1 encoder layer', 4 096 points x batch 2, 6 classes): the product's block-1 network
+    (fc0 + block1 + head) against the oracle's, train mode -- logits within 1e-3 of fp64, every parameter gradient
+    within max(1e-3, 10 x fp32-oracle error), BatchNorm buffers -- and eval mode."""
+    from myria3d_b200 import B200Block1Net, get_neural_net_class
+
+    assert get_neural_net_class("B200Block1Net") is B200Block1Net
+    torch.manual_seed(0)
+    ref = O.OracleBlock1Net(9, 6, knn_method="brute")
+    ref64 = O.OracleBlock1Net(9, 6, knn_method="brute").double()
+    ref64.load_state_dict({k: (v.double() if v.is_floating_point() else v) for k, v in ref.state_dict().items()})
+    net = B200Block1Net(9, 6)
+    net.load_state_dict(ref.state_dict(), strict=True)
+    net.to(DEV)
+    x, pos, y, batch, ptr = O.synthetic_batch([4096, 4096], seed=12345)
+    mask = (torch.rand(8192, 32, generator=torch.Generator().manual_seed(5)) < 0.5).float() * 2.0
+    for m_, mk in ((ref, mask), (ref64, mask.double()), (net, mask.to(DEV))):
+        m_.train()
+        m_.mlp_classif.injected_masks = [None, mk]
+    lr_ = ref(x, pos, batch, ptr)
+    F.cross_entropy(lr_, y).backward()
+    l64 = ref64(x.double(), pos.double(), batch, ptr)
+    F.cross_entropy(l64, y).backward()
+    lg = net(x.to(DEV), pos.to(DEV), batch.to(DEV), ptr.to(DEV))
+    F.cross_entropy(lg, y.to(DEV)).backward()
+    noise = float((lr_.detach().double() - l64.detach()).abs().max())
+    assert_close(lg, l64, atol=max(LOGIT_TOL, 10 * noise), what="config A train logits")
+    g64, g32 = dict(ref64.named_parameters()), dict(ref.named_parameters())
+    for name, p in net.named_parameters():
+        r = g64[name].grad
+        e, e32 = rel_err(p.grad, r), rel_err(g32[name].grad, r)
+        tiny = float((p.grad.cpu().double() - r).abs().max()) < 2e-6
+        assert e < max(1e-3, 10 * e32) or tiny, f"grad {name}: rel err {e:.3e} (fp32 oracle {e32:.3e})"
+    bufs = dict(ref64.named_buffers())
+    for name, b in net.named_buffers():
+        assert_close(b, bufs[name], atol=1e-5, rtol=1e-4, what=name)
+    ref.eval(), net.eval()
+    with torch.no_grad():
+        assert_close(net(x.to(DEV), pos.to(DEV), batch.to(DEV), ptr.to(DEV)), ref(x, pos, batch, ptr), atol=LOGIT_TOL,
+                     what="config A eval logits")
