@@ -303,6 +303,46 @@ int b200_decimation_draw(const int64_t* ptr, const int64_t* new_ptr, int32_t num
 /* *counter += delta (single-thread kernel; device-side step / draw counters of captured graphs). */
 int b200_counter_add(int64_t* counter, int64_t delta, void* stream);
 
+/* ------------------------------------------------------- predict-time sample preparation ------
+ * What myria3d does on the CPU between reading a tile and batching receptive fields, as kernels.  Caller owns all
+ * buffers; *_tmp buffers have the size of their partner; offsets01 is a device int64[2] = {0, n}.
+ *
+ * b200_segmented_sort_pairs: stable ascending LSB radix sort of (key, val) pairs by the low key_bits bits, segment s =
+ *   [offsets[s], offsets[s+1]), one CTA per segment; result in keys / vals (building block of the entries below).
+ * b200_receptive_fields_per_axis / _count / _fill replace split_cloud_into_samples (myria3d/pctl/dataset/utils.py:
+ *   126-158) + get_mosaic_of_centers (:29-38): field f = ix * per_axis + iy has centre (w/2 + ix * (w - overlap),
+ *   w/2 + iy * (w - overlap)) relative to (min_x, min_y) of the cloud; a point belongs to it iff its Chebyshev distance
+ *   to the centre is <= floor(w / 2) (scipy query_ball_point(r = subtile_width // 2, p = inf), tested in float64 like
+ *   scipy).  _count fills counts[per_axis^2] (int64); the caller turns them into offsets (exclusive scan, per_axis^2 + 1
+ *   entries) and _fill writes every field's point indices in ASCENDING order (uint32) at idx[offsets[f] ...]; cursors =
+ *   per_axis^2 uint64 of scratch, pay / pay_tmp / idx_tmp = scratch of sum(counts) uint32.
+ * b200_grid_sampling_sort / _pool replace torch_geometric.transforms.GridSampling(size) for ONE sample
+ *   (configs/datamodule/transforms/preparations/points_budget.yaml:76-79; PyG 2.4 semantics: voxel_grid over
+ *   [pos.min(0), pos.max(0)] = start_end[6] (device), consecutive_cluster -> voxels in ascending id order, scatter MEAN
+ *   of pos and x, majority vote (ties: lowest class) of y).  _sort leaves (voxel id, point index) sorted in key / val,
+ *   head[i] = 1 at the first point of every voxel and *num_voxels; the caller compacts the head positions into
+ *   run_start[num_voxels] (int32) and calls _pool, which writes pos_out / x_out / y_out [num_voxels rows].
+ * b200_random_permutation: perm = a uniformly random permutation of 0..n-1 (Philox keys of b200_decimation_draw +
+ *   sort): perm[:num] is torch.randperm(n)[:num] of MaximumNumNodes / MinimumNumNodes (transforms.py:48-84).
+ * b200_center_pos: pos -= pos.mean(0) for one sample (torch_geometric.transforms.Center, points_budget.yaml:96-97). */
+int b200_segmented_sort_pairs(uint32_t* keys, uint32_t* vals, uint32_t* keys_tmp, uint32_t* vals_tmp,
+                              const int64_t* offsets, int32_t num_segments, int32_t key_bits, void* stream);
+int32_t b200_receptive_fields_per_axis(float tile_width, float subtile_width, float subtile_overlap);
+int b200_receptive_fields_count(const float* pos, int64_t n, float min_x, float min_y, float tile_width,
+                                float subtile_width, float subtile_overlap, int64_t* counts, void* stream);
+int b200_receptive_fields_fill(const float* pos, int64_t n, float min_x, float min_y, float tile_width,
+                               float subtile_width, float subtile_overlap, const int64_t* offsets, uint64_t* cursors,
+                               uint32_t* idx, uint32_t* idx_tmp, uint32_t* pay, uint32_t* pay_tmp, void* stream);
+int b200_grid_sampling_sort(const float* pos, int32_t n, float size, const float* start_end, uint32_t* key, uint32_t* val,
+                            uint32_t* key_tmp, uint32_t* val_tmp, const int64_t* offsets01, int32_t* head,
+                            int32_t* num_voxels, void* stream);
+int b200_grid_sampling_pool(const uint32_t* key, const uint32_t* val, const int32_t* run_start, int32_t num_voxels, int32_t n,
+                            const float* pos, const float* x, int32_t cx, const int64_t* y, int32_t num_classes,
+                            float* pos_out, float* x_out, int64_t* y_out, int32_t* count_out, void* stream);
+int b200_random_permutation(int64_t n, uint64_t seed, const int64_t* counter, uint32_t salt, uint32_t* key, uint32_t* perm,
+                            uint32_t* key_tmp, uint32_t* perm_tmp, const int64_t* offsets01, void* stream);
+int b200_center_pos(float* pos, int32_t n, void* stream);
+
 /* ------------------------------------------------------- tcgen05 self-test --------------
  * d[128, n] (+)= a[128, k] * b[n, k]^T on the 5th-generation tensor cores (tcgen05.mma, TMEM accumulator):
  * passes = 1 plain TF32, 3 = 3xTF32 split (kind::tf32), 6 = bf16 x 3 split (kind::f16, six cross products;

@@ -28,6 +28,14 @@ _SIGNATURES = {
     "b200_adam_flat": (c_int, [_P, _P, _P, _P, c_int64, c_float, _P, c_float, c_float, c_float, _P, _P]),
     "b200_decimation_draw": (c_int, [_P, _P, c_int32, c_int64, ctypes.c_uint64, _P, ctypes.c_uint32, _P, _P]),
     "b200_counter_add": (c_int, [_P, c_int64, _P]),
+    "b200_segmented_sort_pairs": (c_int, [_P, _P, _P, _P, _P, c_int32, c_int32, _P]),
+    "b200_receptive_fields_per_axis": (c_int32, [c_float, c_float, c_float]),
+    "b200_receptive_fields_count": (c_int, [_P, c_int64, c_float, c_float, c_float, c_float, c_float, _P, _P]),
+    "b200_receptive_fields_fill": (c_int, [_P, c_int64, c_float, c_float, c_float, c_float, c_float, _P, _P, _P, _P, _P, _P, _P]),
+    "b200_grid_sampling_sort": (c_int, [_P, c_int32, c_float, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "b200_grid_sampling_pool": (c_int, [_P, _P, _P, c_int32, c_int32, _P, _P, c_int32, _P, c_int32, _P, _P, _P, _P, _P]),
+    "b200_random_permutation": (c_int, [c_int64, ctypes.c_uint64, _P, ctypes.c_uint32, _P, _P, _P, _P, _P, _P]),
+    "b200_center_pos": (c_int, [_P, c_int32, _P]),
     "b200_tc_gemm_selftest": (c_int, [_P, _P, _P, c_int32, c_int32, c_int32, c_int32, _P, _P]),
     "b200_edge_moments": (c_int, [_P, _P, c_int64, c_int32, _P, _P]),
     "b200_lfa_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int64, c_int32, c_int32, _P]),

@@ -190,8 +190,11 @@ def test_product_never_imports_the_oracle():
         assert not _re.search(r"^\s*(from|import)\s+oracle", path.read_text(), _re.M), path
     bench = (root / "bench.py").read_text()
     hits = [m.start() for m in _re.finditer(r"^\s*(from|import)\s+oracle", bench, _re.M)]
-    assert len(hits) == 1  # cpu_reference() only: the cpu_baseline leg and --impl reference
-    assert "def cpu_reference" in bench[:hits[0]] and "def run_reference" not in bench[:hits[0]]
+    # cpu_reference() / cpu_reference_predict() only: the cpu_baseline leg and --impl reference (configs B/E and D)
+    assert len(hits) == 2
+    for h in hits:
+        owner = [m.group(1) for m in _re.finditer(r"^def (\w+)", bench[:h], _re.M)][-1]
+        assert owner in ("cpu_reference", "cpu_reference_predict"), owner
 
 
 def test_fused_decimation_many_clouds_uses_wide_keys():

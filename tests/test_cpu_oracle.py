@@ -230,3 +230,17 @@ def test_oracle_attentive_pooling_identities():
     pooled = O.scatter_sum(s * f, dst, n)
     mean = O.scatter_sum(f, dst, n) / deg[:, None]
     assert_close(pooled, mean, atol=1e-6, what="uniform attention = neighbourhood mean")
+
+
+def test_sample_prep_oracle_pins():
+    """The 8f-4 oracle against the reference's own numbers: 400 receptive fields per km^2 without overlap, 1 521 with a
+    25 m overlap (BASELINE.json configs[3]; pctl/dataset/utils.py:29-38), closed Chebyshev balls, PyG voxel order."""
+    from oracle import sample_prep_oracle as SO
+
+    assert len(SO.get_mosaic_of_centers(1000, 50, 0)) == 400 and len(SO.get_mosaic_of_centers(1000, 50, 25)) == 1521
+    pos = np.array([[0, 0, 0], [25, 25, 1], [50, 50, 2], [75, 25, 3], [100, 100, 0]], dtype=np.float32)
+    fields = SO.split_cloud_into_samples(pos, 100, 50, 0)  # centres (25,25) (25,75) (75,25) (75,75)
+    assert [f.tolist() for f in fields] == [[0, 1, 2], [2], [2, 3], [2, 4]]  # the border point 2 belongs to all four
+    p = torch.tensor([[0.0, 0.0, 0.0], [0.1, 0.1, 0.1], [0.3, 0.0, 0.0], [1.0, 1.0, 1.0]])
+    po, xo, yo, uniq = SO.grid_sampling(p, p.clone(), torch.tensor([2, 1, 0, 1]), 0.25)
+    assert po.shape[0] == 3 and torch.allclose(po[0], torch.tensor([0.05, 0.05, 0.05])) and yo.tolist() == [1, 0, 1]

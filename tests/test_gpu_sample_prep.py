@@ -1,0 +1,98 @@
+"""GPU sample preparation (csrc/sample_prep.cu) vs the CPU oracle (scipy kd-tree ball query, PyG
+GridSampling restated).  Index work is compared bit-exactly."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import sample_prep_oracle as SO
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _cloud(n, width, seed):
+    g = torch.Generator().manual_seed(seed)
+    pos = torch.rand(n, 3, generator=g)
+    pos[:, :2] = pos[:, :2] * width + torch.tensor([650000.0, 6860000.0])[None, :] * 0 + 1000.0  # metric offsets
+    pos[:, 2] = pos[:, 2] * 30.0
+    # points exactly on field borders (closed balls: they belong to both neighbours)
+    pos[:50, 0] = pos[:, 0].min() + torch.arange(50) * (width / 50.0)
+    return pos.float()
+
+
+@pytest.mark.parametrize("tile,sub,overlap,n", [(200.0, 50.0, 0.0, 40000), (200.0, 50.0, 25.0, 40000), (110.0, 50.0, 10.0, 5000),
+                                                (50.0, 50.0, 0.0, 1000)])
+def test_split_cloud_into_samples_bit_exact(lib, tile, sub, overlap, n):
+    from myria3d_b200.sample_prep import split_cloud_into_samples
+
+    pos = _cloud(n, tile, seed=int(tile + overlap))
+    expect = SO.split_cloud_into_samples(pos.numpy(), tile, sub, overlap)
+    got = [t.cpu().numpy() for t in split_cloud_into_samples(pos.to(DEV), tile, sub, overlap)]
+    assert len(got) == len(expect), (len(got), len(expect))
+    for a, b in zip(got, expect):
+        assert np.array_equal(a, b)
+    if overlap == 0.0 and tile == 200.0:
+        assert len(SO.get_mosaic_of_centers(1000, 50, 0)) == 400 and len(SO.get_mosaic_of_centers(1000, 50, 25)) == 1521
+
+
+def test_segmented_sort_pairs(lib):
+    from ctypes import c_void_p
+
+    g = torch.Generator().manual_seed(0)
+    sizes = [0, 1, 5, 1023, 1024, 1025, 70000, 3]
+    off = torch.tensor(np.concatenate([[0], np.cumsum(sizes)]), dtype=torch.int64)
+    total = int(off[-1])
+    keys = torch.randint(0, 2 ** 20, (total,), generator=g, dtype=torch.int64)
+    vals = torch.arange(total, dtype=torch.int64)
+    kd, vd = keys.to(torch.int32).to(DEV), vals.to(torch.int32).to(DEV)
+    kt, vt = torch.empty_like(kd), torch.empty_like(vd)
+    rc = lib.b200_segmented_sort_pairs(c_void_p(kd.data_ptr()), c_void_p(vd.data_ptr()), c_void_p(kt.data_ptr()),
+                                       c_void_p(vt.data_ptr()), c_void_p(off.to(DEV).data_ptr()), len(sizes), 20,
+                                       c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc == 0
+    torch.cuda.synchronize()
+    for s in range(len(sizes)):
+        a, b = int(off[s]), int(off[s + 1])
+        order = torch.sort(keys[a:b], stable=True).indices
+        assert torch.equal(kd[a:b].cpu().long(), keys[a:b][order]) and torch.equal(vd[a:b].cpu().long(), vals[a:b][order])
+
+
+def test_grid_sampling_matches_pyg_semantics(lib):
+    from myria3d_b200.sample_prep import center, grid_sampling
+
+    g = torch.Generator().manual_seed(3)
+    n = 30000
+    pos = torch.rand(n, 3, generator=g) * torch.tensor([50.0, 50.0, 12.0])
+    x = torch.randn(n, 9, generator=g)
+    y = torch.randint(0, 6, (n,), generator=g)
+    ep, ex, ey, uniq = SO.grid_sampling(pos, x, y, 0.25)
+    p, f, lab = grid_sampling(pos.to(DEV), x.to(DEV), y.to(DEV), 0.25)
+    assert p.shape == ep.shape and f.shape == ex.shape, (p.shape, ep.shape)  # same voxels, same order
+    assert float((p.cpu() - ep).abs().max()) < 1e-5 and float((f.cpu() - ex).abs().max()) < 1e-5
+    assert torch.equal(lab.cpu(), ey)
+    c = center(p.clone())
+    assert float((c.cpu() - SO.center(p.cpu())).abs().max()) < 2e-6 * 50
+
+
+def test_budget_draws_and_predict_preparation(lib):
+    from myria3d_b200.sample_prep import maximum_num_nodes, minimum_num_nodes, prepare_predict_sample, random_permutation
+
+    perm = random_permutation(100000, DEV, seed=5, salt=1).cpu()
+    assert torch.equal(perm.sort().values, torch.arange(100000))
+    assert not torch.equal(perm, random_permutation(100000, DEV, seed=5, salt=2).cpu())
+    assert maximum_num_nodes(300, 40000, DEV) is None and minimum_num_nodes(500, 300, DEV) is None
+    ch = maximum_num_nodes(50000, 40000, DEV, seed=1)
+    assert ch.numel() == 40000 and ch.unique().numel() == 40000
+    ch = minimum_num_nodes(70, 300, DEV, seed=1).cpu()
+    assert ch.numel() == 300 and int(ch.max()) < 70 and all(torch.equal(ch[i * 70:(i + 1) * 70].sort().values, torch.arange(70)) for i in range(4))
+    first = torch.zeros(64)
+    for t in range(2000):
+        first[random_permutation(64, DEV, seed=9, salt=t)[0]] += 1
+    assert float(((first - 2000 / 64) ** 2 / (2000 / 64)).sum()) < 120  # chi2(63)
+    g = torch.Generator().manual_seed(1)
+    pos = (torch.rand(80000, 3, generator=g) * torch.tensor([50.0, 50.0, 20.0])).to(DEV)
+    x = torch.randn(80000, 9, generator=g).to(DEV)
+    out = prepare_predict_sample(pos, x)
+    assert out["pos"].shape[0] == out["x"].shape[0] <= 40000 and out["copies"]["pos_copy"].shape[0] == 80000
+    assert float(out["pos"].mean(0).abs().max()) < 1e-3
+    assert torch.allclose(out["copies"]["pos_sampled_copy"] - out["copies"]["pos_sampled_copy"].mean(0), out["pos"], atol=1e-4)
