@@ -44,6 +44,11 @@ size_t accumulate_at_b_workspace_bytes(int ca, int cb, int64_t n);
 int launch_tc_tn(const float* gy, int cout, const float* a1, int64_t ld1, int c1, const float* a2, int64_t ld2, int c2,
                  float* gw, float* gb, int64_t n, float* ws, size_t ws_bytes, cudaStream_t st);
 size_t tc_tn_workspace_bytes(int cout, int ncols, int64_t n);
+// the same contraction for NARROW layers (<= 64 channels, not 64 x 64) on tcgen05 with bf16 x 3 operands read MN-major
+// straight from their row-major layout (tc_skinny.cu)
+bool tc_skinny_tn_ok(int cout, int ktot, bool has_bias, int64_t n);
+int launch_tc_skinny_tn(const float* gy, int cout, const float* a1, int64_t ld1, int c1, const float* a2, int64_t ld2, int c2,
+                        float* gw, float* gb, int64_t n, cudaStream_t st);
 // fused LFA forward / backward with every contraction on tcgen05 (lfa_tc.cu); B200_E_UNSUPPORTED -> use the FMA kernel
 int lfa_tc_fwd_dispatch(const float* x, const float* pos, const int32_t* nbr, const float* enc_w, const float* enc_b,
                         const float* att_wt, float* out, int64_t n, int c, int kt, cudaStream_t st);

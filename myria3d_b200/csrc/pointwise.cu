@@ -496,6 +496,14 @@ static int launch_tn(const float* gy, int cout, const CatRows& A, float* gw, flo
   // >= 64 x 64 outputs: 5th-generation tensor cores (3xTF32), see tc_gemm.cu
   if (tn_uses_tensor_cores(gy, cout, A, gw, n))
     return launch_tc_tn(gy, cout, A.a1, A.ld1, A.c1, A.a2, A.ld2, A.c2, gw, gb, n, ws, ws_bytes, st);
+  {
+    // Narrow layers of levels 0-1.  The warp-streaming FMA kernel below reaches 1.3-1.9 TB/s on its vectorised path
+    // (cout in {16, 32, 64}, float4-addressable rows); odd shapes (mlp1's 32 -> 4, fc0's 9 -> 32) fall to its scalar
+    // path at 0.4-0.8 TB/s: those go to the tensor cores (tc_skinny.cu, measured 33-39 us against 49-85 us).
+    const bool fma_fast = (cout == 16 || cout == 32 || cout == 64) && aligned16(gy) && A.vec;
+    if (!fma_fast && tc_skinny_tn_ok(cout, ktot, gb != nullptr, n))
+      return launch_tc_skinny_tn(gy, cout, A.a1, A.ld1, A.c1, A.a2, A.ld2, A.c2, gw, gb, n, st);
+  }
   if (cout <= 64 && ktot <= 64 && n >= 4096) {
     const bool wide = ktot > 32;
     if (cout <= 16) return wide ? launch_tn_skinny<16, 64>(gy, cout, A, gw, gb, n, st) : launch_tn_skinny<16, 32>(gy, cout, A, gw, gb, n, st);

@@ -20,6 +20,7 @@ graphed = "--graphed" in sys.argv
 from myria3d_b200.optim import FlatAdam
 opt = FlatAdam(model, lr=bench.LR, reducer=red)
 b = bench.host_batch(16, 12800, 12345).to(dev)
+model.model.decimation_rng = "fused"
 step_g = GraphedTrainStep(model, opt, red) if graphed else None
 def step():
     if graphed:

@@ -330,6 +330,42 @@ def test_linear_weight_grad_tensor_cores(lib, n, c1, c2, cout):
     assert rel_err(ag[2].grad, gb_ref) < 5e-6, rel_err(ag[2].grad, gb_ref)
 
 
+@pytest.mark.parametrize("n,c1,c2,cout,bias", [(204800, 32, 0, 4, True), (204800, 9, 0, 32, True), (204800, 32, 0, 33, True),
+                                               (51200, 32, 0, 4, True), (60001, 17, 0, 32, True), (4096, 64, 0, 12, False),
+                                               (204800, 32, 0, 64, True), (7777, 24, 8, 20, True)])
+def test_linear_weight_grad_narrow_tensor_cores(lib, n, c1, c2, cout, bias):
+    """Weight / bias gradients of the narrow level-0/1 layers through tc_skinny.cu (tcgen05 kind::f16 on bf16 x 3
+    operands read MN-major from their row-major layout, K = rows) vs fp64 and vs the FMA fallback: fp32-grade."""
+    from myria3d_b200 import ops
+
+    g = torch.Generator().manual_seed(n + cout)
+    a1 = torch.randn(n, c1, generator=g) + 0.3
+    a2 = torch.randn(n, c2, generator=g) if c2 else None
+    w = torch.randn(cout, c1 + c2, generator=g) / (c1 + c2) ** 0.5
+    b = torch.randn(cout, generator=g) if bias else None
+    gy = torch.randn(n, cout, generator=g)
+    inp = torch.cat([a1, a2], 1) if c2 else a1
+    gw_ref = gy.double().t() @ inp.double()
+    gb_ref = gy.double().sum(0)
+
+    def run():
+        ag = [t.to(DEV).requires_grad_(True) for t in ((a1, w, b) if bias else (a1, w))]
+        y = ops.linear(ag[0], ag[1], ag[2] if bias else None, a2=a2.to(DEV) if c2 else None)
+        y.backward(gy.to(DEV))
+        return ag[1].grad, (ag[2].grad if bias else None)
+
+    gw_tc, gb_tc = run()
+    try:
+        lib.b200_set_option(b"tensor_cores", 0)
+        gw_fma, gb_fma = run()
+    finally:
+        lib.b200_set_option(b"tensor_cores", 1)
+    assert rel_err(gw_tc, gw_ref) < 5e-6, (rel_err(gw_tc, gw_ref), rel_err(gw_fma, gw_ref))
+    assert rel_err(gw_fma, gw_ref) < 5e-6
+    if bias:
+        assert rel_err(gb_tc, gb_ref) < 5e-6 and rel_err(gb_fma, gb_ref) < 5e-6, (rel_err(gb_tc, gb_ref), rel_err(gb_fma, gb_ref))
+
+
 @pytest.mark.parametrize("n,c1,c2,cout", [(5000, 128, 0, 256), (4100, 256, 128, 128), (30000, 64, 0, 64), (3000, 512, 256, 256),
                                           (1030, 64, 0, 70), (1024, 96, 32, 512), (2500, 64, 64, 100), (40000, 32, 0, 128)])
 def test_linear_tensor_core_forward_and_input_grad(lib, n, c1, c2, cout):
