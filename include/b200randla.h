@@ -345,13 +345,14 @@ int b200_center_pos(float* pos, int32_t n, void* stream);
 
 /* ------------------------------------------------------- tcgen05 self-test --------------
  * d[128, n] (+)= a[128, k] * b[n, k]^T on the 5th-generation tensor cores (tcgen05.mma, TMEM accumulator):
- * passes = 1 plain TF32, 3 = 3xTF32 split (kind::tf32), 6 = bf16 x 3 split (kind::f16, six cross products;
- * the arithmetic of the fused LFA kernels); 3 and 6 are fp32-grade.  Pins the shared-memory descriptor / TMEM
+ * passes = 1 plain TF32, 3 = 3xTF32 split (kind::tf32), 6 = bf16 x 3 split (kind::f16, six cross products: the
+ * arithmetic of tc_skinny.cu), 2 = fp16 x 2 split (kind::f16, three cross products: the arithmetic of the fused LFA
+ * kernels); 2, 3 and 6 are fp32-grade.  Pins the shared-memory descriptor / TMEM
  * conventions of the fused kernels (no reference counterpart: test infrastructure of the kernels that replace
  * pyg_randla_net.py:97-152).  flags: bit 0 / bit 1 = stage A / B transposed and read it through the MN-major
- * descriptor (passes = 6 only); bit 2 = pre-initialise the accumulator from d with tcgen05.st and accumulate.
+ * descriptor (passes = 2 or 6); bit 2 = pre-initialise the accumulator from d with tcgen05.st and accumulate.
  * *status (device int32): 0 = ok, 1 = the MMA completion barrier timed out.
- * 16 <= n <= 256, n % 16 == 0, k % 8 == 0 (k % 16 == 0 for passes = 6). */
+ * 16 <= n <= 256, n % 16 == 0, k % 8 == 0 (k % 16 == 0 for passes = 2 or 6); flags < 16 (bit 3: A in tensor memory). */
 int b200_tc_gemm_selftest(const float* a, const float* b, float* d, int32_t n, int32_t k, int32_t passes,
                           int32_t flags, int32_t* status, void* stream);
 

@@ -53,8 +53,8 @@ int launch_tc_skinny_tn(const float* gy, int cout, const float* a1, int64_t ld1,
 int lfa_tc_fwd_dispatch(const float* x, const float* pos, const int32_t* nbr, const float* enc_w, const float* enc_b,
                         const float* att_wt, float* out, int64_t n, int c, int kt, cudaStream_t st);
 int lfa_tc_bwd_dispatch(const float* x, const float* pos, const int32_t* nbr, const float* enc_w, const float* enc_b,
-                        const float* att_w, const float* go, float* gx, float* gew, float* geb, float* gaw, int64_t n, int c,
-                        int kt, cudaStream_t st);
+                        const float* att_w, const float* att_wt, const float* go, float* gx, float* gew, float* geb, float* gaw,
+                        void* ws, int64_t n, int c, int kt, cudaStream_t st);
 bool lfa_tc_supported(int c, int kt);
 // row-streaming NT GEMM on tcgen05 (tc_nt.cu): out[i][m] = sum_k [a1|a2][i][k] * wm[m][k] + bias[m], channels of the
 // output split over two destination segments; colstats: fp64 (sum, sum of squares) per row tile [tiles][2 * mrows]

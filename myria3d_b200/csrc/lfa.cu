@@ -782,7 +782,9 @@ extern "C" int b200_lfa_fwd(const float* x, const float* pos, const int32_t* nbr
 }
 
 extern "C" int64_t b200_lfa_bwd_workspace_bytes(int64_t n, int32_t c, int32_t kt) {
-  if (n <= 0 || c < 64 || b200::lfa_tc_supported(c, kt)) return 0;  // tensor-core path: dW_att stays in TMEM
+  if (n <= 0) return 0;
+  if (b200::lfa_tc_supported(c, kt)) return 256;  // tensor-core path: dW_att stays in TMEM; one scratch word (max |grad_out|)
+  if (c < 64) return 0;
   return 2 * n * (int64_t)kt * c * (int64_t)sizeof(float) + (int64_t)b200::accumulate_at_b_workspace_bytes(c, c, n * kt);
 }
 
@@ -804,8 +806,8 @@ extern "C" int b200_lfa_bwd(const float* x, const float* pos, const int32_t* nbr
                (long long)b200_lfa_bwd_workspace_bytes(n, c, kt));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   {  // c in {32, 64, 128}: every contraction on the tensor cores (lfa_tc.cu)
-    const int rc = lfa_tc_bwd_dispatch(x, pos, nbr, enc_w, enc_b, att_w, grad_out, grad_x, grad_enc_w, grad_enc_b,
-                                       grad_att_w, n, c, kt, st);
+    const int rc = lfa_tc_bwd_dispatch(x, pos, nbr, enc_w, enc_b, att_w, att_wt, grad_out, grad_x, grad_enc_w, grad_enc_b,
+                                       grad_att_w, workspace, n, c, kt, st);
     if (rc != B200_E_UNSUPPORTED) return rc;
   }
   float* ws = static_cast<float*>(workspace);

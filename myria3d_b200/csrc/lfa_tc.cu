@@ -1,5 +1,5 @@
 // Fused LocSE + attentive pooling, FORWARD and BACKWARD, with every contraction on the 5th-generation tensor cores
-// (tcgen05.mma kind::f16 on bf16 x 3 split operands = fp32-grade products, accumulators in TMEM) -- the
+// (tcgen05.mma kind::f16 on fp16 x 2 split operands = fp32-grade products, accumulators in TMEM) -- the
 // c in {32, 64, 128} levels of LocalFeatureAggregation (myria3d/models/modules/pyg_randla_net.py:121-152).
 // Production path of b200_lfa_fwd / b200_lfa_bwd for these widths; narrower levels (c = 8, 16: K = 8 / 16
 // contractions) and c = 256 stay on the FMA kernels of lfa.cu.
@@ -15,8 +15,13 @@
 // synchronised with named barriers only, so the tensor-core phases of one slot overlap the gather / epilogue phases
 // of the other; W_att (the largest operand) is staged once and shared.
 //
-// Operands are bf16 x 3 (t1, t2, t3 with v = t1 + t2 + t3; six cross products per contraction):
-//     W_att  in TENSOR MEMORY as the A operand (lanes = replicated row, 3 planes of c/2 columns): "Wk" = W[n][m] for
+// Operands are fp16 x 2 (v = hi + lo, three cross products hi*hi + lo*hi + hi*lo per contraction: 2^-22 relative in
+// fp16's normal range).  The data is kept in that range by construction: F = BatchNorm + LeakyReLU outputs and the
+// encoding (O(1)); W_att is staged as 16 * W; the softmax gradient dA is multiplied by a power of two derived from
+// max |grad_out| (one 4-byte reduction kernel in front of the backward), undone when the results leave the SM.
+// (bf16 x 3 with six products was measured first: same accuracy, twice the tensor-core instructions and 1.5x the
+// shared memory -- the backward was tensor-pipe bound at 49 + N/2 cycles per instruction.)
+//     W_att  in TENSOR MEMORY as the A operand (lanes = replicated row, 2 planes of c/2 columns): "Wk" = W[n][m] for
 //            MMA1 and, for c <= 64, "Wm" = W^T for MMA3 (c = 128: MMA3 reads a shared-memory copy MN-major).  Staged
 //            once per CTA with tcgen05.st; only the B operand travels from shared memory per instruction
 //            (measured: 22 + N/2 cycles per M128 x N x K16 instruction against 50 + N/2 with A in shared memory).
@@ -63,25 +68,25 @@ struct LtcPlan {
   static constexpr int WORKERS = R * LTC_WPQ;      // (replica, warp-of-quadrant) pairs sharing a tile's centres
   static constexpr int CPT = TC / WORKERS;         // centres per epilogue thread and tile
   // W_att lives in TENSOR MEMORY as the A operand of MMA1 (lanes = replicated n, K = m: "Wk") and, for c <= 64, of
-  // MMA3 (lanes = replicated m, K = n: "Wm"): 3 planes of C/2 columns each (two bf16 per column).  Only for c = 128,
+  // MMA3 (lanes = replicated m, K = n: "Wm"): 2 planes of C/2 columns each (two fp16 per column).  Only for c = 128,
   // where both do not fit beside the accumulators, MMA3 reads Wm from shared memory (MN-major view of W_att[n][m]).
   static constexpr bool WM_IN_TMEM = (C <= 64);
   static constexpr int M4 = (C == 128) ? 128 : 64;  // M of the dW tile (MMA4)
   static constexpr uint32_t W_PLANE_COLS = C / 2;
-  static constexpr uint32_t W_COLS = 3 * W_PLANE_COLS * ((BWD && WM_IN_TMEM) ? 2 : 1);
+  static constexpr uint32_t W_COLS = 2 * W_PLANE_COLS * ((BWD && WM_IN_TMEM) ? 2 : 1);
   static constexpr size_t WM_PLANE = (BWD && !WM_IN_TMEM) ? (size_t)(C / 8) * (C + 1) * 16 : 0;  // rows n, chunks m
   static constexpr size_t F_PLANE = (size_t)(C / 8) * (NE + 1) * 16;
   static constexpr size_t DA_PLANE = (size_t)(NE / 8) * (C + 1) * 16;
   static constexpr size_t T_BYTES = tc::operand_floats(NE, H) * 4;  // fp32 [H/4][NE+1][4]: x-gradient transposition
   // shared part
   static constexpr size_t OFF_WM = 0;
-  static constexpr size_t OFF_EW = OFF_WM + 3 * WM_PLANE;
+  static constexpr size_t OFF_EW = OFF_WM + 2 * WM_PLANE;
   static constexpr size_t SHARED_BYTES = OFF_EW + 16 * 17 * (size_t)(H / 8);  // [H/8][17] float4 (1 pad)
   // per-slot part: dA | F | T | Q P | NB DEG.  The M = 128 read of the dA planes (c < 128 rows) runs past the end of
   // the last chunk into the next plane / F (garbage in dW lanes >= c that nobody reads): F follows dA.
   static constexpr size_t S_DA = 0;
-  static constexpr size_t S_F = S_DA + (BWD ? 3 * DA_PLANE : 0);
-  static constexpr size_t S_T = S_F + 3 * F_PLANE;
+  static constexpr size_t S_F = S_DA + (BWD ? 2 * DA_PLANE : 0);
+  static constexpr size_t S_T = S_F + 2 * F_PLANE;
   static constexpr size_t S_Q = S_T + (BWD ? T_BYTES : 0);
   static constexpr size_t S_P = S_Q + 16 * (size_t)NE;
   static constexpr size_t S_NB = S_P + 16 * (size_t)TC;
@@ -110,26 +115,48 @@ __device__ __forceinline__ void slot_sync(int slot) {
   asm volatile("bar.sync %0, %1;" ::"r"(1 + slot), "r"(LTC_SLOT_THREADS) : "memory");
 }
 
-// 8 fp32 values -> three 16-byte vectors of bf16 terms
-__device__ __forceinline__ void split8_bf16x3(const float (&v)[8], uint4& p1, uint4& p2, uint4& p3) {
-  uint32_t t1[8], t2[8], t3[8];
+constexpr float kWScale = 16.f;  // W_att is staged as 16 * W (exact): typical weights land in fp16's normal range
+constexpr float kLog2eOverWScale = 1.4426950408889634f / kWScale;
+
+// 4-byte scratch word of the backward: bit pattern of max |grad_out| (non-negative floats order like unsigned ints)
+__global__ void __launch_bounds__(256)
+lfa_absmax_kernel(const float* __restrict__ g, int64_t count, uint32_t* __restrict__ out) {
+  float m = 0.f;
+  const int64_t n4 = count / 4;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (int64_t)gridDim.x * 256) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(g) + i);
+    m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+  }
+  for (int64_t i = n4 * 4 + (int64_t)blockIdx.x * 256 + threadIdx.x; i < count; i += (int64_t)gridDim.x * 256) m = fmaxf(m, fabsf(g[i]));
 #pragma unroll
-  for (int u = 0; u < 8; ++u) tc::split_bf16x3(v[u], t1[u], t2[u], t3[u]);
-  p1 = make_uint4(tc::pack_hi16(t1[0], t1[1]), tc::pack_hi16(t1[2], t1[3]), tc::pack_hi16(t1[4], t1[5]), tc::pack_hi16(t1[6], t1[7]));
-  p2 = make_uint4(tc::pack_hi16(t2[0], t2[1]), tc::pack_hi16(t2[2], t2[3]), tc::pack_hi16(t2[4], t2[5]), tc::pack_hi16(t2[6], t2[7]));
-  p3 = make_uint4(tc::pack_hi16(t3[0], t3[1]), tc::pack_hi16(t3[2], t3[3]), tc::pack_hi16(t3[4], t3[5]), tc::pack_hi16(t3[6], t3[7]));
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out, __float_as_uint(m));
 }
 
 template <int C, int NE, int KT, bool BWD>
 __global__ void __launch_bounds__(LTC_THREADS, 1)
 lfa_tc_kernel(const float* __restrict__ x, const float* __restrict__ pos, const int32_t* __restrict__ nbr,
               const float* __restrict__ enc_w, const float* __restrict__ enc_b,
-              const float* __restrict__ att_w /* backward: W_att [n][m]; forward: att_wt [m][n] */,
+              const float* __restrict__ att_w /* backward: W_att [n][m] (may be null in the forward) */,
+              const float* __restrict__ att_wt /* att_wt [m][n] = W_att[n][m] */,
               float* __restrict__ out,                                                   // forward
               const float* __restrict__ grad_out, float* __restrict__ grad_x,            // backward
               float* __restrict__ grad_enc_w, float* __restrict__ grad_enc_b, float* __restrict__ grad_att_w,
+              const uint32_t* __restrict__ absmax_bits /* backward: max |grad_out| as float bits */,
               int64_t n, int64_t ntiles, long long* __restrict__ dbg) {
   using Plan = LtcPlan<C, NE, KT, BWD>;
+  // power-of-two scale of the softmax gradient (backward): gscale = 2^(128 - e) for max |grad_out| in [2^(e-127), 2^(e-126))
+  float gscale = 1.f, inv_gscale = 1.f;
+  if constexpr (BWD) {
+    const uint32_t e = (*absmax_bits) >> 23;
+    if (e >= 24u && e <= 250u) {
+      gscale = __uint_as_float((255u - e) << 23);
+      inv_gscale = __uint_as_float((e - 1u) << 23);
+    }
+  }
+  const float inv_dscale = inv_gscale / (kWScale * kWScale);  // dF accumulator carries gscale * kWScale^2
+  inv_gscale /= kWScale;                                     // dW accumulator carries gscale * kWScale
+  (void)inv_dscale;
   constexpr int H = Plan::H, H8 = Plan::H8, TC = Plan::TC, R = Plan::R, CPT = Plan::CPT;
   constexpr int ST = LTC_SLOT_THREADS;
   extern __shared__ __align__(128) unsigned char ltc_smem[];
@@ -139,13 +166,13 @@ lfa_tc_kernel(const float* __restrict__ x, const float* __restrict__ pos, const 
   const int tid = threadIdx.x, slot = tid / ST, stid = tid % ST;
   const int swarp = stid >> 5, lane = tid & 31;
 
-  unsigned char* Wm = ltc_smem + Plan::OFF_WM;  // 3 planes (backward, c = 128 only)
+  unsigned char* Wm = ltc_smem + Plan::OFF_WM;  // 2 planes (backward, c = 128 only)
   // encoder weights [H/8 channel groups][8 channels][2]: (w0..w3), (w4, w5, w6, bias); one float4 of padding per
   // group: the H/8 groups read together by a quarter-warp of the build land in different banks
   float4* EW = reinterpret_cast<float4*>(ltc_smem + Plan::OFF_EW);
   unsigned char* sbase = ltc_smem + Plan::SHARED_BYTES + (size_t)slot * Plan::SLOT_BYTES;
-  unsigned char* dAp = sbase + Plan::S_DA;  // 3 planes of DA_PLANE bytes
-  unsigned char* Fp = sbase + Plan::S_F;    // 3 planes of F_PLANE bytes
+  unsigned char* dAp = sbase + Plan::S_DA;  // 2 planes of DA_PLANE bytes
+  unsigned char* Fp = sbase + Plan::S_F;    // 2 planes of F_PLANE bytes
   float* T = reinterpret_cast<float*>(sbase + Plan::S_T);
   float4* Q = reinterpret_cast<float4*>(sbase + Plan::S_Q);  // (p_j, dist) per edge
   float4* P = reinterpret_cast<float4*>(sbase + Plan::S_P);  // p_i per centre
@@ -166,10 +193,13 @@ lfa_tc_kernel(const float* __restrict__ x, const float* __restrict__ pos, const 
       const float4 a = __ldg(reinterpret_cast<const float4*>(att_w + (int64_t)nn * C + 8 * j));
       const float4 b = __ldg(reinterpret_cast<const float4*>(att_w + (int64_t)nn * C + 8 * j + 4));
       const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-      uint4 p[3];
-      split8_bf16x3(v, p[0], p[1], p[2]);
+      float vs[8];
 #pragma unroll
-      for (int t = 0; t < 3; ++t)
+      for (int u = 0; u < 8; ++u) vs[u] = v[u] * kWScale;
+      uint4 p[2];
+      tc::split8_f16x2(vs, p[0], p[1]);
+#pragma unroll
+      for (int t = 0; t < 2; ++t)
         *reinterpret_cast<uint4*>(Wm + t * Plan::WM_PLANE + ((size_t)j * (C + 1) + nn) * 16) = p[t];
     }
   }
@@ -190,8 +220,8 @@ lfa_tc_kernel(const float* __restrict__ x, const float* __restrict__ pos, const 
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
-  const uint32_t tmem_wk = tmem_slot;                                   // A of MMA1: 3 planes x C/2 columns
-  const uint32_t tmem_wm = tmem_slot + 3 * Plan::W_PLANE_COLS;          // A of MMA3 (c <= 64, backward)
+  const uint32_t tmem_wk = tmem_slot;                                   // A of MMA1: 2 planes x C/2 columns
+  const uint32_t tmem_wm = tmem_slot + 2 * Plan::W_PLANE_COLS;          // A of MMA3 (c <= 64, backward)
   const uint32_t tmem_s = tmem_slot + Plan::W_COLS + (uint32_t)slot * Plan::SLOT_COLS;  // scores S / dF accumulator
   const uint32_t tmem_dw = tmem_s + (uint32_t)NE;                        // dW accumulator: C columns (backward)
   uint64_t* bar1 = &bars[slot][0];
@@ -216,18 +246,18 @@ lfa_tc_kernel(const float* __restrict__ x, const float* __restrict__ pos, const 
   const int worker = (tl / C) * LTC_WPQ + wq;
   const uint32_t lane_base = (uint32_t)(lq * 32) << 16;
   // ---- W_att into tensor memory (slot 0: the first warp of each lane quadrant writes Wk, the second one Wm).
-  // lane tl holds row (tl % C): Wk[n][k = m] = W_att[n][m], Wm[m][k = n] = W_att[n][m].  The backward gets
-  // att_w = W_att row-major, the forward ABI only carries att_wt[m][n] = W_att[n][m].
+  // lane tl holds row (tl % C): Wk[n][k = m] = W_att[n][m], Wm[m][k = n] = W_att[n][m].
   if (slot == 0 && (wq == 0 || (BWD && Plan::WM_IN_TMEM))) {
     const bool is_wk = (wq == 0);
-    // element (row = ch, k) sits at att_w[ch * C + k] or at att_w[k * C + ch]
-    const bool row_contig = BWD ? is_wk : false;
+    // lane = row ch of the operand; consecutive lanes read consecutive addresses in both cases:
+    //   Wk[n][k = m] = W_att[n][m] = att_wt[m * C + n],   Wm[m][k = n] = W_att[n][m] = att_w[n * C + m]
+    const float* src = is_wk ? att_wt : att_w;
 #pragma unroll 1
     for (int k0 = 0; k0 < C; k0 += 32) {
       float v[32];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = row_contig ? __ldg(att_w + (int64_t)ch * C + k0 + i) : __ldg(att_w + (int64_t)(k0 + i) * C + ch);
-      tc::tmem_st_row32_bf16x3((is_wk ? tmem_wk : tmem_wm) + lane_base + (uint32_t)k0 / 2, Plan::W_PLANE_COLS, v);
+      for (int i = 0; i < 32; ++i) v[i] = kWScale * __ldg(src + (int64_t)(k0 + i) * C + ch);
+      tc::tmem_st_row32_f16x2((is_wk ? tmem_wk : tmem_wm) + lane_base + (uint32_t)k0 / 2, Plan::W_PLANE_COLS, v);
     }
     tc::tmem_st_wait();
   }
@@ -318,12 +348,11 @@ lfa_tc_kernel(const float* __restrict__ x, const float* __restrict__ pos, const 
             v[u] = lrelu(s, kLReluSlope);
           }
         }
-        uint4 p1, p2, p3;
-        split8_bf16x3(v, p1, p2, p3);
+        uint4 p1, p2;
+        tc::split8_f16x2(v, p1, p2);
         const size_t off = ((size_t)(H8 + c8) * (NE + 1) + e) * 16;
         *reinterpret_cast<uint4*>(Fp + off) = p1;
         *reinterpret_cast<uint4*>(Fp + Plan::F_PLANE + off) = p2;
-        *reinterpret_cast<uint4*>(Fp + 2 * Plan::F_PLANE + off) = p3;
       }
     }
     // ---- B2 (consume): F[:, 0:H)
@@ -333,12 +362,11 @@ lfa_tc_kernel(const float* __restrict__ x, const float* __restrict__ pos, const 
       if ((NE * H8) % ST == 0 || t < NE * H8) {
         const int e = t / H8, m8 = t % H8;
         const float v[8] = {xa[it].x, xa[it].y, xa[it].z, xa[it].w, xb[it].x, xb[it].y, xb[it].z, xb[it].w};
-        uint4 p1, p2, p3;
-        split8_bf16x3(v, p1, p2, p3);
+        uint4 p1, p2;
+        tc::split8_f16x2(v, p1, p2);
         const size_t off = ((size_t)m8 * (NE + 1) + e) * 16;
         *reinterpret_cast<uint4*>(Fp + off) = p1;
         *reinterpret_cast<uint4*>(Fp + Plan::F_PLANE + off) = p2;
-        *reinterpret_cast<uint4*>(Fp + 2 * Plan::F_PLANE + off) = p3;
       }
     }
     tc::fence_smem_to_async();
@@ -347,15 +375,15 @@ lfa_tc_kernel(const float* __restrict__ x, const float* __restrict__ pos, const 
     tc::fence_after_sync();
     LTC_TS();
 
-    // ---- MMA1: S[n][e] = sum_m W[n][m] F[e][m]   (six bf16 cross products)
+    // ---- MMA1: S[n][e] = sum_m W[n][m] F[e][m]   (three fp16 cross products)
     if (swarp == 0) {
       if (tc::elect_one_sync()) {
-        constexpr uint32_t idesc = tc::idesc_bf16(128, NE);
+        constexpr uint32_t idesc = tc::idesc_f16(128, NE);
         const uint64_t bd0 = tc::plane_desc_k_base(smem_u32(Fp), NE);
 #pragma unroll
-        for (int pass = 0; pass < 6; ++pass) {
-          const uint32_t a_tmem = tmem_wk + (uint32_t)tc::bf16x3_term_a(pass) * Plan::W_PLANE_COLS;
-          const uint64_t bd = tc::desc_advance(bd0, (uint32_t)(tc::bf16x3_term_b(pass) * Plan::F_PLANE));
+        for (int pass = 0; pass < 3; ++pass) {
+          const uint32_t a_tmem = tmem_wk + (uint32_t)tc::f16x2_term_a(pass) * Plan::W_PLANE_COLS;
+          const uint64_t bd = tc::desc_advance(bd0, (uint32_t)(tc::f16x2_term_b(pass) * Plan::F_PLANE));
 #pragma unroll
           for (int k0 = 0; k0 < C; k0 += 16)
             tc::mma_bf16_ts(tmem_s, a_tmem + (uint32_t)k0 / 2, tc::desc_advance(bd, (k0 / 16) * tc::plane_k_step_bytes(NE)), idesc,
@@ -383,7 +411,7 @@ lfa_tc_kernel(const float* __restrict__ x, const float* __restrict__ pos, const 
       }
       const int64_t i = tile_base + g;
       // the fp32 feature of (edge, this channel): gathered x_j or the recomputed encoding (same operation order as
-      // the build: bit-identical to the value the tensor core saw, before the bf16 x 3 split)
+      // the build: bit-identical to the value the tensor core saw, before the fp16 split)
       if (ch < H) {
 #pragma unroll
         for (int k = 0; k < KT; ++k) {
@@ -406,10 +434,12 @@ lfa_tc_kernel(const float* __restrict__ x, const float* __restrict__ pos, const 
 #pragma unroll
       for (int k = 0; k < KT; ++k)
         if (FULL || k < deg) mx = fmaxf(mx, a[k]);
+      const float neg_mx = -mx * kLog2eOverWScale;
       float sum = 0.f, o = 0.f;
 #pragma unroll
       for (int k = 0; k < KT; ++k) {
-        const float p = (FULL || k < deg) ? __expf(a[k] - mx) : 0.f;
+        // (scores carry kWScale: exp(a / 16 - mx / 16) as one FFMA + ex2)
+        const float p = (FULL || k < deg) ? tc::ex2_approx(fmaf(a[k], kLog2eOverWScale, neg_mx)) : 0.f;
         a[k] = p;
         sum += p;
         o = fmaf(p, f[k], o);
@@ -419,22 +449,25 @@ lfa_tc_kernel(const float* __restrict__ x, const float* __restrict__ pos, const 
       if constexpr (!BWD) {
         if (i < n) out[i * C + ch] = o;
       } else {
-        const float gi = (i < n) ? inv * __ldg(grad_out + i * C + ch) : 0.f;
+        // everything downstream of grad_out carries the power-of-two gscale (max |grad_out| * gscale in [2, 4), times kWScale below): the
+        // softmax gradient then sits in fp16's normal range whatever the loss scale is; undone in E3 / the dW flush
+        // dA is stored as kWScale * gscale * dA: the accumulators of MMA3 / MMA4 then carry kWScale^2 * gscale and
+        // kWScale * gscale (3 instead of 4 operations per edge here)
+        const float gi = (i < n) ? inv * __ldg(grad_out + i * C + ch) * (gscale * kWScale) : 0.f;
 #pragma unroll
         for (int k8 = 0; k8 < KT; k8 += 8) {
           float da[8];
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
-            const float sg = a[k8 + u] * gi;  // s * go: direct term of dF (0 for invalid edges: p = 0)
-            da[u] = sg * (f[k8 + u] - o);     // gradient w.r.t. the score
-            a[k8 + u] = sg;
+            const float sg = a[k8 + u] * gi;  // kWScale * s * go (0 for invalid edges: p = 0)
+            da[u] = sg * (f[k8 + u] - o);     // kWScale * gradient w.r.t. the score
+            a[k8 + u] = sg * kWScale;         // direct term of dF at the accumulator's scale kWScale^2 * gscale
           }
-          uint4 p1, p2, p3;
-          split8_bf16x3(da, p1, p2, p3);
+          uint4 p1, p2;
+          tc::split8_f16x2(da, p1, p2);
           const size_t off = ((size_t)((g * KT + k8) >> 3) * (C + 1) + ch) * 16;
           *reinterpret_cast<uint4*>(dAp + off) = p1;
           *reinterpret_cast<uint4*>(dAp + Plan::DA_PLANE + off) = p2;
-          *reinterpret_cast<uint4*>(dAp + 2 * Plan::DA_PLANE + off) = p3;
         }
 #pragma unroll
         for (int k0 = 0; k0 < KT; k0 += 16) {
@@ -472,22 +505,22 @@ lfa_tc_kernel(const float* __restrict__ x, const float* __restrict__ pos, const 
         if (tc::elect_one_sync()) {
           const uint64_t da_mn0 = tc::plane_desc_mn_base(smem_u32(dAp), C);
           if constexpr (Plan::WM_IN_TMEM) {
-            constexpr uint32_t idesc = tc::idesc_bf16(128, NE, /*a_mn=*/false, /*b_mn=*/true);
+            constexpr uint32_t idesc = tc::idesc_f16(128, NE, /*a_mn=*/false, /*b_mn=*/true);
 #pragma unroll
-            for (int pass = 0; pass < 6; ++pass) {
-              const uint32_t a_tmem = tmem_wm + (uint32_t)tc::bf16x3_term_a(pass) * Plan::W_PLANE_COLS;
-              const uint64_t bd = tc::desc_advance(da_mn0, (uint32_t)(tc::bf16x3_term_b(pass) * Plan::DA_PLANE));
+            for (int pass = 0; pass < 3; ++pass) {
+              const uint32_t a_tmem = tmem_wm + (uint32_t)tc::f16x2_term_a(pass) * Plan::W_PLANE_COLS;
+              const uint64_t bd = tc::desc_advance(da_mn0, (uint32_t)(tc::f16x2_term_b(pass) * Plan::DA_PLANE));
 #pragma unroll
               for (int k0 = 0; k0 < C; k0 += 16)
                 tc::mma_bf16_ts(tmem_s, a_tmem + (uint32_t)k0 / 2, tc::desc_advance(bd, (k0 / 16) * tc::kPlaneMnStepBytes), idesc, true);
             }
           } else {
-            constexpr uint32_t idesc = tc::idesc_bf16(128, NE, /*a_mn=*/true, /*b_mn=*/true);
+            constexpr uint32_t idesc = tc::idesc_f16(128, NE, /*a_mn=*/true, /*b_mn=*/true);
             const uint64_t wm0 = tc::plane_desc_mn_base(smem_u32(Wm), C);
 #pragma unroll
-            for (int pass = 0; pass < 6; ++pass) {
-              const uint64_t ad = tc::desc_advance(wm0, (uint32_t)(tc::bf16x3_term_a(pass) * Plan::WM_PLANE));
-              const uint64_t bd = tc::desc_advance(da_mn0, (uint32_t)(tc::bf16x3_term_b(pass) * Plan::DA_PLANE));
+            for (int pass = 0; pass < 3; ++pass) {
+              const uint64_t ad = tc::desc_advance(wm0, (uint32_t)(tc::f16x2_term_a(pass) * Plan::WM_PLANE));
+              const uint64_t bd = tc::desc_advance(da_mn0, (uint32_t)(tc::f16x2_term_b(pass) * Plan::DA_PLANE));
 #pragma unroll
               for (int k0 = 0; k0 < C; k0 += 16)
                 tc::mma_bf16(tmem_s, tc::desc_advance(ad, (k0 / 16) * tc::kPlaneMnStepBytes),
@@ -497,13 +530,13 @@ lfa_tc_kernel(const float* __restrict__ x, const float* __restrict__ pos, const 
           tc::mma_commit(bar3);
           {
             // c <= 64: an M = 64 tile (half the A-operand traffic; rows land in lanes (n % 16) + 32 * (n / 16))
-            constexpr uint32_t idesc = tc::idesc_bf16(Plan::M4, C, /*a_mn=*/false, /*b_mn=*/true);
+            constexpr uint32_t idesc = tc::idesc_f16(Plan::M4, C, /*a_mn=*/false, /*b_mn=*/true);
             const uint64_t da_k0 = tc::plane_desc_k_base(smem_u32(dAp), C);
             const uint64_t f_mn0 = tc::plane_desc_mn_base(smem_u32(Fp), NE);
 #pragma unroll
-            for (int pass = 0; pass < 6; ++pass) {
-              const uint64_t ad = tc::desc_advance(da_k0, (uint32_t)(tc::bf16x3_term_a(pass) * Plan::DA_PLANE));
-              const uint64_t bd = tc::desc_advance(f_mn0, (uint32_t)(tc::bf16x3_term_b(pass) * Plan::F_PLANE));
+            for (int pass = 0; pass < 3; ++pass) {
+              const uint64_t ad = tc::desc_advance(da_k0, (uint32_t)(tc::f16x2_term_a(pass) * Plan::DA_PLANE));
+              const uint64_t bd = tc::desc_advance(f_mn0, (uint32_t)(tc::f16x2_term_b(pass) * Plan::F_PLANE));
 #pragma unroll
               for (int k0 = 0; k0 < NE; k0 += 16)
                 tc::mma_bf16(tmem_dw, tc::desc_advance(ad, (k0 / 16) * tc::plane_k_step_bytes(C)),
@@ -533,7 +566,7 @@ lfa_tc_kernel(const float* __restrict__ x, const float* __restrict__ pos, const 
         if (ch < H) {
           const int toff = ((ch >> 2) * (NE + 1) + g * KT) * 4 + (ch & 3);
 #pragma unroll
-          for (int k = 0; k < KT; ++k) T[toff + 4 * k] = d[k];
+          for (int k = 0; k < KT; ++k) T[toff + 4 * k] = d[k] * inv_dscale;
         } else {
           const float4 p = P[g];
           const float sp = fmaf(mw0.z, p.z, fmaf(mw0.y, p.y, fmaf(mw0.x, p.x, mw1.w)));
@@ -545,7 +578,7 @@ lfa_tc_kernel(const float* __restrict__ x, const float* __restrict__ pos, const 
               float s = sp;  // lrelu'(z) from the recomputed pre-activation
               s = fmaf(mw0.w, q.x, s), s = fmaf(mw1.x, q.y, s), s = fmaf(mw1.y, q.z, s);
               s = fmaf(mw1.z, q.w, s);
-              const float dz = d[k] * (s > 0.f ? 1.f : kLReluSlope);
+              const float dz = d[k] * (s > 0.f ? inv_dscale : inv_dscale * kLReluSlope);
               gw[3] = fmaf(dz, q.x, gw[3]);
               gw[4] = fmaf(dz, q.y, gw[4]);
               gw[5] = fmaf(dz, q.z, gw[5]);
@@ -582,7 +615,9 @@ lfa_tc_kernel(const float* __restrict__ x, const float* __restrict__ pos, const 
             if ((Plan::M4 == 128 || (tl & 31) < 16) && n_row < C) {
               float4* dst = reinterpret_cast<float4*>(grad_att_w + (int64_t)n_row * C + c0);
 #pragma unroll
-              for (int u = 0; u < 4; ++u) atomicAdd(dst + u, make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]));
+              for (int u = 0; u < 4; ++u)
+                atomicAdd(dst + u, make_float4(v[4 * u] * inv_gscale, v[4 * u + 1] * inv_gscale, v[4 * u + 2] * inv_gscale,
+                                               v[4 * u + 3] * inv_gscale));
             }
           }
         }
@@ -633,8 +668,8 @@ lfa_tc_kernel(const float* __restrict__ x, const float* __restrict__ pos, const 
 
 template <int C, int NE, int KT, bool BWD>
 static int launch_lfa_tc(const float* x, const float* pos, const int32_t* nbr, const float* enc_w, const float* enc_b,
-                         const float* att_w, float* out, const float* go, float* gx, float* gew, float* geb, float* gaw,
-                         int64_t n, cudaStream_t st) {
+                         const float* att_w, const float* att_wt, float* out, const float* go, float* gx, float* gew, float* geb,
+                         float* gaw, const uint32_t* absmax, int64_t n, cudaStream_t st) {
   using Plan = LtcPlan<C, NE, KT, BWD>;
   auto kern = lfa_tc_kernel<C, NE, KT, BWD>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Plan::SMEM_BYTES);
@@ -642,16 +677,16 @@ static int launch_lfa_tc(const float* x, const float* pos, const int32_t* nbr, c
   const int64_t ntiles = ceil_div(n, Plan::TC);
   int64_t grid = num_sms();  // one persistent CTA per SM (TMEM: every CTA allocates up to all 512 columns)
   if (grid > ceil_div(ntiles, LTC_SLOTS)) grid = ceil_div(ntiles, LTC_SLOTS);
-  kern<<<(unsigned)grid, LTC_THREADS, Plan::SMEM_BYTES, st>>>(x, pos, nbr, enc_w, enc_b, att_w, out, go, gx, gew, geb, gaw, n,
-                                                             ntiles, tc_debug_buffer());
+  kern<<<(unsigned)grid, LTC_THREADS, Plan::SMEM_BYTES, st>>>(x, pos, nbr, enc_w, enc_b, att_w, att_wt, out, go, gx, gew, geb, gaw,
+                                                             absmax, n, ntiles, tc_debug_buffer());
   B200_CHECK_LAUNCH("lfa_tc_kernel");
   return B200_OK;
 }
 
 // (C, KT, NE forward, NE backward).  Tile sizes: every epilogue thread gets >= 1 centre (NE / KT a multiple of
-// 2 * 128 / C), shared memory <= 227 KB, 2 * (NE + C) TMEM columns <= 512.
+// 2 * 128 / C), shared memory <= 227 KB, W columns + 2 * (NE + C) TMEM columns <= 512.
 // K = 32 neighbour tables (BASELINE configs[4]) would need twice the shared memory per centre: FMA kernels.
-#define B200_LFA_TC_CASES(X) X(32, 16, 128, 128) X(64, 16, 128, 64) X(128, 16, 64, 32)
+#define B200_LFA_TC_CASES(X) X(32, 16, 128, 128) X(64, 16, 128, 128) X(128, 16, 128, 32)
 
 // returns B200_E_UNSUPPORTED when this (c, kt) has no tensor-core kernel (the caller then uses the FMA kernel)
 int lfa_tc_fwd_dispatch(const float* x, const float* pos, const int32_t* nbr, const float* enc_w, const float* enc_b,
@@ -659,19 +694,30 @@ int lfa_tc_fwd_dispatch(const float* x, const float* pos, const int32_t* nbr, co
   if (!tensor_cores_enabled()) return B200_E_UNSUPPORTED;
 #define X(C_, KT_, NEF_, NEB_)                                                                                     \
   if (c == C_ && kt == KT_)                                                                                        \
-    return launch_lfa_tc<C_, NEF_, KT_, false>(x, pos, nbr, enc_w, enc_b, att_wt, out, nullptr, nullptr, nullptr, \
-                                               nullptr, nullptr, n, st);
+    return launch_lfa_tc<C_, NEF_, KT_, false>(x, pos, nbr, enc_w, enc_b, nullptr, att_wt, out, nullptr, nullptr, nullptr, \
+                                               nullptr, nullptr, nullptr, n, st);
   B200_LFA_TC_CASES(X)
 #undef X
   return B200_E_UNSUPPORTED;
 }
 
+// ws: >= 4 bytes of device scratch (the maximum |grad_out| of this call)
 int lfa_tc_bwd_dispatch(const float* x, const float* pos, const int32_t* nbr, const float* enc_w, const float* enc_b,
-                        const float* att_w, const float* go, float* gx, float* gew, float* geb, float* gaw, int64_t n, int c,
-                        int kt, cudaStream_t st) {
-  if (!tensor_cores_enabled()) return B200_E_UNSUPPORTED;
+                        const float* att_w, const float* att_wt, const float* go, float* gx, float* gew, float* geb, float* gaw, void* ws, int64_t n,
+                        int c, int kt, cudaStream_t st) {
+  if (!lfa_tc_supported(c, kt)) return B200_E_UNSUPPORTED;
+  uint32_t* absmax = static_cast<uint32_t*>(ws);
+  cudaError_t e = cudaMemsetAsync(absmax, 0, sizeof(uint32_t), st);
+  if (e != cudaSuccess) return cuda_fail(e, "lfa_tc absmax memset");
+  {
+    int64_t blocks = ceil_div(n * c / 4 + 1, 256);
+    if (blocks > (int64_t)num_sms() * 8) blocks = (int64_t)num_sms() * 8;
+    lfa_absmax_kernel<<<(unsigned)blocks, 256, 0, st>>>(go, n * c, absmax);
+    B200_CHECK_LAUNCH("lfa_absmax_kernel");
+  }
 #define X(C_, KT_, NEF_, NEB_) \
-  if (c == C_ && kt == KT_) return launch_lfa_tc<C_, NEB_, KT_, true>(x, pos, nbr, enc_w, enc_b, att_w, nullptr, go, gx, gew, geb, gaw, n, st);
+  if (c == C_ && kt == KT_)    \
+    return launch_lfa_tc<C_, NEB_, KT_, true>(x, pos, nbr, enc_w, enc_b, att_w, att_wt, nullptr, go, gx, gew, geb, gaw, absmax, n, st);
   B200_LFA_TC_CASES(X)
 #undef X
   return B200_E_UNSUPPORTED;

@@ -9,6 +9,7 @@
 // LBO = R + 1 units (one k-chunk of ALL rows, padded by 16 B so that lanes reading the same row at different
 // k-chunks hit different banks).  The array is therefore  float smem[K/4][R+1][4].
 #pragma once
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 #include "common.cuh"
@@ -95,6 +96,35 @@ __host__ __device__ constexpr uint32_t idesc_bf16(int m, int n, bool a_mn = fals
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
          ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
+
+// instruction descriptor: D fp32, A/B fp16, dense
+__host__ __device__ constexpr uint32_t idesc_f16(int m, int n, bool a_mn = false, bool b_mn = false) {
+  return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+// fp16 x 2 split (round to nearest): v = hi + lo + r, hi = fp16(v), lo = fp16(v - hi) (v - hi is exact in fp32).  Three
+// products hi*hi', lo*hi', hi*lo' reproduce the fp32 product to ~2^-22 for operands in fp16's NORMAL range
+// (6.1e-5 <= |v| <= 65504; the caller keeps them there: O(1) data, power-of-two pre-scaling); below it the absolute
+// error is bounded by the subnormal spacing (<= 3e-8).  Half the planes and half the instructions of bf16 x 3.
+// Two values at a time: the packed words hold (v0 | v1 << 16).
+__device__ __forceinline__ void split_f16x2_pair(float v0, float v1, uint32_t& hi, uint32_t& lo) {
+  v0 = fminf(fmaxf(v0, -60000.f), 60000.f);
+  v1 = fminf(fmaxf(v1, -60000.f), 60000.f);
+  const __half2 h = __floats2half2_rn(v0, v1);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+__device__ __forceinline__ void split8_f16x2(const float (&v)[8], uint4& ph, uint4& pl) {
+  split_f16x2_pair(v[0], v[1], ph.x, pl.x);
+  split_f16x2_pair(v[2], v[3], ph.y, pl.y);
+  split_f16x2_pair(v[4], v[5], ph.z, pl.z);
+  split_f16x2_pair(v[6], v[7], ph.w, pl.w);
+}
+// which part (0 = hi, 1 = lo) of A / B the p-th of the three passes multiplies
+__device__ __forceinline__ constexpr int f16x2_term_a(int p) { return p == 1 ? 1 : 0; }
+__device__ __forceinline__ constexpr int f16x2_term_b(int p) { return p == 2 ? 1 : 0; }
 
 // bf16 x 3 split by truncation: v = t1 + t2 + t3 + r with |r| <= 2^-24 |v|; every t_i is exactly a bf16 (the high
 // half of an fp32 word), every residual is exact in fp32.  The six products t1t1', t1t2', t2t1', t2t2', t1t3', t3t1'
@@ -225,6 +255,19 @@ __device__ __forceinline__ void tmem_st_row32_bf16x3(uint32_t taddr, uint32_t pl
   tmem_st16u(taddr, w[0]);
   tmem_st16u(taddr + plane_cols, w[1]);
   tmem_st16u(taddr + 2 * plane_cols, w[2]);
+}
+// the same for fp16 x 2 operands: 2 planes
+__device__ __forceinline__ void tmem_st_row32_f16x2(uint32_t taddr, uint32_t plane_cols, const float (&v)[32]) {
+  uint32_t w[2][16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) split_f16x2_pair(v[2 * i], v[2 * i + 1], w[0][i], w[1][i]);
+  tmem_st16u(taddr, w[0]);
+  tmem_st16u(taddr + plane_cols, w[1]);
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 

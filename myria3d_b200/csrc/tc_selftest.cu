@@ -3,8 +3,9 @@
 // into one TMEM accumulator.  Not on the hot path: it exists so that the descriptor / layout / tcgen05.ld /
 // tcgen05.st conventions used by the fused kernels are pinned by a test against an fp64 product.
 //
-// passes = 1 / 3: kind::tf32 (plain / 3xTF32);  passes = 6: kind::f16 with bf16 x 3 operands (six cross products),
-// the arithmetic of the fused LFA kernels.
+// passes = 1 / 3: kind::tf32 (plain / 3xTF32);  passes = 6: kind::f16 with bf16 x 3 operands (six cross products, the
+// arithmetic of tc_skinny.cu);  passes = 2: kind::f16 with fp16 x 2 operands (three cross products, the arithmetic of
+// the fused LFA kernels; operands in fp16's normal range).
 // flags:  bit 0  A is staged "transposed" (buffer rows = k, 16-byte vectors along the 128 rows of A) and read
 //                through the MN-major descriptor -- the way lfa_tc.cu re-reads dA / W_att without moving them
 //                (bf16 only: a no-swizzle MN-major tf32 operand is not readable, see tc.cuh);
@@ -105,8 +106,8 @@ tc_gemm_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B
   if (warp == 0) tc::tmem_dealloc(tmem_d, tmem_cols);
 }
 
-template <int KC>  // KC > 0: k is the compile-time constant KC and the issue loop is unrolled (scripts/mma_probe.py)
-__global__ void __launch_bounds__(128)
+template <int KC, bool F16>  // KC > 0: k is the compile-time constant KC and the issue loop is unrolled (scripts/mma_probe.py)
+__global__ void __launch_bounds__(128)                                  // F16: fp16 x 2 planes / 3 products instead of bf16 x 3 / 6
 tc_gemm_selftest_bf16_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ D, int n, int k,
                              int flags, uint32_t tmem_cols, int* __restrict__ status, long long* __restrict__ dbg) {
   extern __shared__ __align__(128) uint16_t tcs16[];
@@ -123,17 +124,29 @@ tc_gemm_selftest_bf16_kernel(const float* __restrict__ A, const float* __restric
 
   for (int t = tid; t < 128 * k; t += 128) {
     const int r = t % 128, kk = t / 128;
-    uint32_t t1, t2, t3;
-    tc::split_bf16x3(A[r * k + kk], t1, t2, t3);
     const int off = a_mn ? tc::plane_offset(k, kk, r) : tc::plane_offset(128, r, kk);
-    Ap[off] = (uint16_t)(t1 >> 16), Ap[a_plane + off] = (uint16_t)(t2 >> 16), Ap[2 * a_plane + off] = (uint16_t)(t3 >> 16);
+    if constexpr (F16) {
+      uint32_t hi, lo;
+      tc::split_f16x2_pair(A[r * k + kk], 0.f, hi, lo);
+      Ap[off] = (uint16_t)hi, Ap[a_plane + off] = (uint16_t)lo;
+    } else {
+      uint32_t t1, t2, t3;
+      tc::split_bf16x3(A[r * k + kk], t1, t2, t3);
+      Ap[off] = (uint16_t)(t1 >> 16), Ap[a_plane + off] = (uint16_t)(t2 >> 16), Ap[2 * a_plane + off] = (uint16_t)(t3 >> 16);
+    }
   }
   for (int t = tid; t < n * k; t += 128) {
     const int r = t % n, kk = t / n;
-    uint32_t t1, t2, t3;
-    tc::split_bf16x3(B[r * k + kk], t1, t2, t3);
     const int off = b_mn ? tc::plane_offset(k, kk, r) : tc::plane_offset(n, r, kk);
-    Bp[off] = (uint16_t)(t1 >> 16), Bp[b_plane + off] = (uint16_t)(t2 >> 16), Bp[2 * b_plane + off] = (uint16_t)(t3 >> 16);
+    if constexpr (F16) {
+      uint32_t hi, lo;
+      tc::split_f16x2_pair(B[r * k + kk], 0.f, hi, lo);
+      Bp[off] = (uint16_t)hi, Bp[b_plane + off] = (uint16_t)lo;
+    } else {
+      uint32_t t1, t2, t3;
+      tc::split_bf16x3(B[r * k + kk], t1, t2, t3);
+      Bp[off] = (uint16_t)(t1 >> 16), Bp[b_plane + off] = (uint16_t)(t2 >> 16), Bp[2 * b_plane + off] = (uint16_t)(t3 >> 16);
+    }
   }
   if (warp == 0) tc::tmem_alloc(&tmem_slot, tmem_cols);
   if (tid == 0) {
@@ -153,7 +166,10 @@ tc_gemm_selftest_bf16_kernel(const float* __restrict__ A, const float* __restric
       float v[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] = A[tid * k + k0 + i];
-      tc::tmem_st_row32_bf16x3(tmem_a + ((uint32_t)(warp * 32) << 16) + (uint32_t)k0 / 2, a_cols, v);
+      if constexpr (F16)
+        tc::tmem_st_row32_f16x2(tmem_a + ((uint32_t)(warp * 32) << 16) + (uint32_t)k0 / 2, a_cols, v);
+      else
+        tc::tmem_st_row32_bf16x3(tmem_a + ((uint32_t)(warp * 32) << 16) + (uint32_t)k0 / 2, a_cols, v);
     }
   }
   if (init_d) {
@@ -174,7 +190,7 @@ tc_gemm_selftest_bf16_kernel(const float* __restrict__ A, const float* __restric
   long long t0 = 0;
   if (warp == 0) {
     if (tc::elect_one_sync()) {
-      const uint32_t idesc = tc::idesc_bf16(128, n, a_mn, b_mn);
+      const uint32_t idesc = F16 ? tc::idesc_f16(128, n, a_mn, b_mn) : tc::idesc_bf16(128, n, a_mn, b_mn);
       const uint64_t ad0 = a_mn ? tc::plane_desc_mn_base(smem_u32(Ap), a_rows) : tc::plane_desc_k_base(smem_u32(Ap), a_rows);
       const uint64_t bd0 = b_mn ? tc::plane_desc_mn_base(smem_u32(Bp), b_rows) : tc::plane_desc_k_base(smem_u32(Bp), b_rows);
       const uint32_t a_step = a_mn ? tc::kPlaneMnStepBytes : tc::plane_k_step_bytes(a_rows);
@@ -182,21 +198,22 @@ tc_gemm_selftest_bf16_kernel(const float* __restrict__ A, const float* __restric
       bool acc = init_d;
       t0 = clock64();
       auto one = [&](int pass, int ks) {
-        const uint64_t ad = tc::desc_advance(ad0, (uint32_t)(tc::bf16x3_term_a(pass) * a_plane * 2) + ks * a_step);
-        const uint64_t bd = tc::desc_advance(bd0, (uint32_t)(tc::bf16x3_term_b(pass) * b_plane * 2) + ks * b_step);
+        const int ta = F16 ? tc::f16x2_term_a(pass) : tc::bf16x3_term_a(pass), tb = F16 ? tc::f16x2_term_b(pass) : tc::bf16x3_term_b(pass);
+        const uint64_t ad = tc::desc_advance(ad0, (uint32_t)(ta * a_plane * 2) + ks * a_step);
+        const uint64_t bd = tc::desc_advance(bd0, (uint32_t)(tb * b_plane * 2) + ks * b_step);
         if (a_tmem)
-          tc::mma_bf16_ts(tmem_d, tmem_a + (uint32_t)tc::bf16x3_term_a(pass) * a_cols + (uint32_t)ks * 8, bd, idesc, acc);
+          tc::mma_bf16_ts(tmem_d, tmem_a + (uint32_t)ta * a_cols + (uint32_t)ks * 8, bd, idesc, acc);
         else
           tc::mma_bf16(tmem_d, ad, bd, idesc, acc);
         acc = true;
       };
       if constexpr (KC > 0) {
 #pragma unroll
-        for (int pass = 0; pass < 6; ++pass)
+        for (int pass = 0; pass < (F16 ? 3 : 6); ++pass)
 #pragma unroll
           for (int ks = 0; ks < KC / 16; ++ks) one(pass, ks);
       } else {
-        for (int pass = 0; pass < 6; ++pass)
+        for (int pass = 0; pass < (F16 ? 3 : 6); ++pass)
           for (int ks = 0; ks < k / 16; ++ks) one(pass, ks);
       }
       tc::mma_commit(&bar);
@@ -229,13 +246,13 @@ using namespace b200;
 extern "C" int b200_tc_gemm_selftest(const float* a, const float* b, float* d, int32_t n, int32_t k, int32_t passes,
                                      int32_t flags, int32_t* status, void* stream) {
   B200_REQUIRE(a && b && d && status, B200_E_INVALID, "b200_tc_gemm_selftest: null pointer");
-  B200_REQUIRE(n >= 16 && n <= 256 && n % 16 == 0 && k >= 8 && k % 8 == 0 && (passes == 1 || passes == 3 || passes == 6) &&
+  B200_REQUIRE(n >= 16 && n <= 256 && n % 16 == 0 && k >= 8 && k % 8 == 0 && (passes == 1 || passes == 2 || passes == 3 || passes == 6) &&
                    flags >= 0 && flags < 16,
                B200_E_INVALID,
-               "b200_tc_gemm_selftest: need 16 <= n <= 256 (multiple of 16), k multiple of 8, passes in {1, 3, 6}, flags < 16");
+               "b200_tc_gemm_selftest: need 16 <= n <= 256 (multiple of 16), k multiple of 8, passes in {1, 2, 3, 6}, flags < 16");
   uint32_t cols = 32;
   while ((int)cols < n) cols <<= 1;
-  if (passes == 6) {
+  if (passes == 6 || passes == 2) {
     B200_REQUIRE(k % 16 == 0, B200_E_INVALID, "b200_tc_gemm_selftest: bf16 operands need k %% 16 == 0");
     if (flags & 8) {
       B200_REQUIRE(k % 32 == 0 && !(flags & 1) && n + 3 * k / 2 <= 512, B200_E_INVALID,
@@ -248,7 +265,8 @@ extern "C" int b200_tc_gemm_selftest(const float* a, const float* b, float* d, i
     // planes are read exactly
     const size_t smem = sizeof(uint16_t) * 3 * (a_plane + b_plane);
     B200_REQUIRE(smem <= 200 * 1024, B200_E_UNSUPPORTED, "b200_tc_gemm_selftest: operands need %zu bytes of shared memory", smem);
-    auto kern = (k == 64) ? tc_gemm_selftest_bf16_kernel<64> : tc_gemm_selftest_bf16_kernel<0>;
+    auto kern = (passes == 2) ? ((k == 64) ? tc_gemm_selftest_bf16_kernel<64, true> : tc_gemm_selftest_bf16_kernel<0, true>)
+                              : ((k == 64) ? tc_gemm_selftest_bf16_kernel<64, false> : tc_gemm_selftest_bf16_kernel<0, false>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, "tc selftest smem attribute");
     kern<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(a, b, d, n, k, flags, cols, status, tc_debug_buffer());

@@ -32,13 +32,13 @@ att_w = torch.randn(c, c, device=dev) / c ** 0.5
 att_wt = att_w.t().contiguous()
 out, go = torch.empty(nt, c, device=dev), torch.randn(nt, c, device=dev)
 gx, gew, geb, gaw = torch.zeros_like(x), torch.zeros_like(enc_w), torch.zeros_like(enc_b), torch.zeros_like(att_w)
-ws = torch.empty(16, dtype=torch.uint8, device=dev)
+ws = torch.empty(max(256, int(lib.b200_lfa_bwd_workspace_bytes(nt, c, 16))), dtype=torch.uint8, device=dev)
 
 def fwd():
     _lib.check(lib.b200_lfa_fwd(_p(x), _p(pos), _p(nbr), _p(enc_w), _p(enc_b), _p(att_wt), _p(out), nt, c, 16, _stream()), "fwd")
 def bwd():
     _lib.check(lib.b200_lfa_bwd(_p(x), _p(pos), _p(nbr), _p(enc_w), _p(enc_b), _p(att_wt), _p(att_w), _p(go), _p(gx), _p(gew),
-                                _p(geb), _p(gaw), _p(ws), 0, nt, c, 16, _stream()), "bwd")
+                                _p(geb), _p(gaw), _p(ws), ws.numel(), nt, c, 16, _stream()), "bwd")
 
 for name, fn, per_tile in (("fwd", fwd, 4), ("bwd", bwd, 7)):
     fn(); torch.cuda.synchronize()
