@@ -485,7 +485,7 @@ static int launch_tn_skinny(const float* gy, int cout, const CatRows& A, float* 
 
 // generic dispatcher of gw[cout, c1+c2] += gy^T [a1|a2], gb += colsum(gy)
 static bool tn_uses_tensor_cores(const float* gy, int cout, const CatRows& A, const float* gw, int64_t n) {
-  return cout >= 64 && A.c1 + A.c2 >= 64 && n >= 1024 && cout % 4 == 0 && A.vec && aligned16(gy) && aligned16(gw) &&
+  return cout >= 64 && A.c1 + A.c2 >= 64 && n >= 512 && cout % 4 == 0 && A.vec && aligned16(gy) && aligned16(gw) &&
          tensor_cores_enabled();
 }
 
@@ -916,7 +916,9 @@ extern "C" int b200_linear_fwd(const float* a1, int64_t ld1, int32_t c1, const f
 
 // Input gradients go to the tensor cores below level 1 only: on >= 51 200 rows the layers are HBM-bound and the FMA
 // kernel (no transpose pass, no idle TMEM lanes for narrow outputs) is as fast or faster (profiles/).
-static bool bwd_input_uses_tc(int64_t n, int ktot, int cout) { return n <= 32768 && tc_nt_shape_ok(n, cout, 0, ktot); }
+static bool bwd_input_uses_tc(int64_t n, int ktot, int cout) {
+  return n >= 1024 && n <= 32768 && tc_nt_shape_ok(n, cout, 0, ktot);
+}
 
 extern "C" int64_t b200_linear_bwd_input_workspace_bytes(int64_t n, int32_t c1, int32_t c2, int32_t cout) {
   return bwd_input_uses_tc(n, c1 + c2, cout) ? (int64_t)(c1 + c2) * cout * (int64_t)sizeof(float) : 0;

@@ -298,10 +298,14 @@ static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) 
 // sizes only (the statistics-partial count must be known before the launch): see b200_linear_fwd_num_stat_partials
 bool tc_nt_shape_ok(int64_t n, int c1, int c2, int mrows) {
   const int ktot = c1 + c2;
-  return tensor_cores_enabled() && n >= 1024 && mrows >= 64 && ktot >= 32 && ktot % TNT_KC == 0 && c1 % TNT_KC == 0;
+  return tensor_cores_enabled() && n >= 512 && mrows >= 64 && ktot >= 32 && ktot % TNT_KC == 0 && c1 % TNT_KC == 0;
 }
-int tc_nt_rows_per_tile(int64_t n, int mrows) {  // 128-row tiles only while they all fit one wave of CTAs
-  return (ceil_div(n, 128) * ceil_div(mrows, 128) > num_sms()) ? 256 : 128;
+int tc_nt_rows_per_tile(int64_t n, int mrows) {
+  // 128-row tiles only while they all fit one wave of CTAs; 64-row tiles when 128-row ones would leave more than
+  // half of the SMs idle (levels 3-4: 3 200 / 800 rows)
+  const int64_t tiles128 = ceil_div(n, 128) * ceil_div(mrows, 128);
+  if (tiles128 > num_sms()) return 256;
+  return (2 * tiles128 <= num_sms()) ? 64 : 128;
 }
 
 template <int BN>
@@ -328,7 +332,9 @@ int launch_tc_nt(const float* a1, int64_t ld1, int c1, const float* a2, int64_t 
                "tensor-core linear layer: activation rows and weights must be 16-byte aligned (row strides %% 4 == 0)");
   const NtRows X{a1, ld1, c1, a2, ld2, c2};
   const NtOut O{o1, old1, oc1, o2, old2};
-  if (tc_nt_rows_per_tile(n, mrows) == 256) return launch_tc_nt_bn<256>(X, wm, mrows, bias, O, colstats, n, st);
+  const int rows = tc_nt_rows_per_tile(n, mrows);
+  if (rows == 256) return launch_tc_nt_bn<256>(X, wm, mrows, bias, O, colstats, n, st);
+  if (rows == 64) return launch_tc_nt_bn<64>(X, wm, mrows, bias, O, colstats, n, st);
   return launch_tc_nt_bn<128>(X, wm, mrows, bias, O, colstats, n, st);
 }
 

@@ -47,6 +47,25 @@ def _call(name: str, *args) -> None:
 # buffers of FlatGradAllReducer (and so of FlatAdam / GraphedTrainStep, which are built on it).
 _DIRECT_GRAD_STORAGES: set = set()
 
+# Fork/join of independent backward kernels (weight gradient || input gradient of one Linear) onto a second stream.
+# Only while a CUDA graph is being captured: the fork then becomes two parallel branches of the graph (the kernels of
+# levels 2-4 fill a fraction of the 148 SMs each and run side by side); in eager mode the event traffic would only
+# add host time.
+PARALLEL_BACKWARD = True
+_SIDE_STREAMS: dict = {}
+
+
+def _side_stream(device: torch.device) -> "torch.cuda.Stream":
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    s = _SIDE_STREAMS.get(key)
+    if s is None:
+        s = _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return s
+
+
+def _fork_backward() -> bool:
+    return PARALLEL_BACKWARD and torch.cuda.is_current_stream_capturing()
+
 
 def enable_direct_grads(flat: Tensor) -> None:
     """Allow the backward kernels to accumulate parameter gradients straight into views of ``flat``."""
@@ -426,13 +445,20 @@ class _Linear(torch.autograd.Function):
         lib = _lib.load()
         ga1 = torch.empty_like(a1) if ctx.needs_input_grad[0] else None
         ga2 = torch.empty_like(a2) if (a2 is not None and ctx.needs_input_grad[1]) else None
-        if ga1 is not None or ga2 is not None:
+        want_input = ga1 is not None or ga2 is not None
+        want_weight = ctx.needs_input_grad[2] or (ctx.has_bias and ctx.needs_input_grad[3])
+
+        def input_grad():
             nb = int(lib.b200_linear_bwd_input_workspace_bytes(n, c1, c2, cout))
             wsi = torch.empty(nb, dtype=torch.uint8, device=w.device) if nb else None
             _call("b200_linear_bwd_input", _p(grad_y), _p(w), _p(ga1), c1, c1, _p(ga2), c2, c2, _p(wsi), nb, n, cout,
                   _stream())
+
+        fork = want_input and want_weight and _fork_backward()
+        if want_input and not fork:
+            input_grad()
         gw = gb = None
-        if ctx.needs_input_grad[2] or (ctx.has_bias and ctx.needs_input_grad[3]):
+        if want_weight:
             dw = _direct_grad(ctx.w_param)
             db = _direct_grad(ctx.b_param) if ctx.has_bias else None
             direct = dw is not None and (not ctx.has_bias or db is not None)
@@ -443,8 +469,19 @@ class _Linear(torch.autograd.Function):
                 gb_buf = gb = torch.zeros(cout, dtype=torch.float32, device=w.device) if ctx.has_bias else None
             nbytes = int(lib.b200_linear_bwd_weight_workspace_bytes(n, c1, c2, cout, 1 if ctx.has_bias else 0))
             ws = torch.empty(nbytes, dtype=torch.uint8, device=w.device) if nbytes else None
-            _call("b200_linear_bwd_weight", _p(grad_y), _p(a1), c1, c1, _p(a2), c2, c2, _p(gw_buf), _p(gb_buf), _p(ws),
-                  nbytes, n, cout, _stream())
+            if fork:
+                # every buffer both branches touch was allocated (and zero-filled) on the main stream above and stays
+                # referenced until the join below, so the caching allocator cannot hand it out in between
+                main, side = torch.cuda.current_stream(), _side_stream(w.device)
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    _call("b200_linear_bwd_weight", _p(grad_y), _p(a1), c1, c1, _p(a2), c2, c2, _p(gw_buf), _p(gb_buf),
+                          _p(ws), nbytes, n, cout, _stream())
+                input_grad()
+                main.wait_stream(side)
+            else:
+                _call("b200_linear_bwd_weight", _p(grad_y), _p(a1), c1, c1, _p(a2), c2, c2, _p(gw_buf), _p(gb_buf),
+                      _p(ws), nbytes, n, cout, _stream())
         return ga1, ga2, gw, gb, None
 
 

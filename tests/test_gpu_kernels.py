@@ -308,7 +308,7 @@ def test_linear_stats_cancellation(lib):
 
 
 @pytest.mark.parametrize("n,c1,c2,cout", [(5000, 128, 0, 256), (4100, 256, 128, 128), (20000, 64, 0, 64), (3000, 512, 256, 256),
-                                          (1030, 64, 0, 70), (9000, 96, 0, 512)])
+                                          (1030, 64, 0, 70), (9000, 96, 0, 512), (800, 512, 0, 512), (600, 512, 256, 256)])
 def test_linear_weight_grad_tensor_cores(lib, n, c1, c2, cout):
     """Weight / bias gradients through the tcgen05 3xTF32 split-K kernel (tc_gemm.cu) vs fp64: fp32-grade."""
     from myria3d_b200 import ops
@@ -367,7 +367,8 @@ def test_linear_weight_grad_narrow_tensor_cores(lib, n, c1, c2, cout, bias):
 
 
 @pytest.mark.parametrize("n,c1,c2,cout", [(5000, 128, 0, 256), (4100, 256, 128, 128), (30000, 64, 0, 64), (3000, 512, 256, 256),
-                                          (1030, 64, 0, 70), (1024, 96, 32, 512), (2500, 64, 64, 100), (40000, 32, 0, 128)])
+                                          (1030, 64, 0, 70), (1024, 96, 32, 512), (2500, 64, 64, 100), (40000, 32, 0, 128),
+                                          (800, 512, 0, 512), (700, 512, 256, 256), (513, 64, 0, 64)])
 def test_linear_tensor_core_forward_and_input_grad(lib, n, c1, c2, cout):
     """Layers with >= 64 input and output channels run on tcgen05 (tc_nt.cu, 3xTF32, channels on TMEM lanes): output,
     BatchNorm column statistics and input gradients against fp64 -- fp32-grade (rel 2e-6), ragged last row tile,
