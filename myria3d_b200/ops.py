@@ -67,6 +67,16 @@ def _fork_backward() -> bool:
     return PARALLEL_BACKWARD and torch.cuda.is_current_stream_capturing()
 
 
+def fork_enabled() -> bool:
+    """True while a CUDA graph is being captured (and PARALLEL_BACKWARD is on): independent kernel chains may then be
+    enqueued on :func:`side_stream` between ``side.wait_stream(main)`` and ``main.wait_stream(side)`` / events."""
+    return _fork_backward()
+
+
+def side_stream(device: torch.device) -> "torch.cuda.Stream":
+    return _side_stream(device)
+
+
 def enable_direct_grads(flat: Tensor) -> None:
     """Allow the backward kernels to accumulate parameter gradients straight into views of ``flat``."""
     _DIRECT_GRAD_STORAGES.add(flat.untyped_storage().data_ptr())

@@ -165,13 +165,19 @@ class DilatedResidualBlock(nn.Module):
         self.lfa2 = LocalFeatureAggregation(d_out // 2)
         self.last_nbr: Optional[Tensor] = None
 
-    def forward(self, x: Tensor, pos: Tensor, level: _Level) -> Tensor:
+    def graph(self, pos: Tensor, level: _Level):
+        """knn_graph(pos, k, batch, loop=True) (:180) once per block, shared by both LFAs, + the fp64 edge moments the
+        folded encoder BatchNorm needs in training."""
         k = self.num_neighbors
-        # knn_graph(pos, k, batch, loop=True) (:180) once per block, shared by both LFAs
         nbr, _ = ops.knn(pos, level.ptr, pos, level.ptr, k, level.max_n, kt=ops.table_width(k), want_dist=False)
-        self.last_nbr = nbr
-        num_edges = level.num_edges(k)
         moments = ops.edge_moments(pos, nbr) if self.training else None
+        return nbr, moments
+
+    def forward(self, x: Tensor, pos: Tensor, level: _Level, geometry: Optional["_Geometry"] = None, lvl_idx: int = 0) -> Tensor:
+        k = self.num_neighbors
+        num_edges = level.num_edges(k)
+        if geometry is None:
+            nbr, moments = self.graph(pos, level)
 
         sc_lin, sc_bn = self.shortcut.lins[0], self.shortcut.norms[0].module
         m2_lin, m2_bn = self.mlp2.lins[0], self.mlp2.norms[0].module
@@ -180,6 +186,9 @@ class DilatedResidualBlock(nn.Module):
         else:
             y_sc, st_sc = ops.linear(x, sc_lin.weight, sc_lin.bias), None
         h = self.mlp1(x)  # :183
+        if geometry is not None:  # built ahead (possibly on a second stream): the shortcut and mlp1 did not need it
+            nbr, moments = geometry.graph_of(lvl_idx)
+        self.last_nbr = nbr
         h = self.lfa1(h, pos, nbr, moments, num_edges)  # :184
         h = self.lfa2(h, pos, nbr, moments, num_edges)  # :185
         if self.training:
@@ -238,11 +247,50 @@ class FPModule(nn.Module):
         self.k = k
         self.nn = net
 
-    def forward(self, x: Tensor, pos: Tensor, level: _Level, x_skip: Tensor, pos_skip: Tensor, level_skip: _Level) -> Tensor:
-        nbr, dist2 = ops.knn(pos, level.ptr, pos_skip, level_skip.ptr, self.k, level_skip.max_n, kt=self.k,
-                             max_points_per_cloud=level.max_n)
+    def table(self, pos: Tensor, level: _Level, pos_skip: Tensor, level_skip: _Level):
+        """The k nearest coarse points of every fine point and their squared distances (knn_interpolate's search)."""
+        return ops.knn(pos, level.ptr, pos_skip, level_skip.ptr, self.k, level_skip.max_n, kt=self.k,
+                       max_points_per_cloud=level.max_n)
+
+    def forward(self, x: Tensor, pos: Tensor, level: _Level, x_skip: Tensor, pos_skip: Tensor, level_skip: _Level,
+                table=None) -> Tensor:
+        nbr, dist2 = table if table is not None else self.table(pos, level, pos_skip, level_skip)
         xi = ops.knn_interpolate_from_table(x, nbr, dist2, self.k)  # :250
         return self.nn(xi, x_skip)  # cat + SharedMLP (:251-252) without materialising the cat
+
+
+class _Geometry:
+    """Everything of a forward pass that depends on the POSITIONS only: per level the kNN graph, its edge moments, the
+    decimation draw, the decimated positions and the decoder's interpolation tables.  None of it needs the features, so
+    :meth:`B200RandLANet._geometry` computes it ahead of the encoder -- while a CUDA graph is being captured on a second
+    stream, as a parallel branch that runs next to the feature kernels (kNN is latency-bound, the Linear / BatchNorm
+    passes are HBM-bound).  ``ready[l]`` is recorded on that stream once level ``l`` is complete."""
+
+    def __init__(self):
+        self.pos: List[Tensor] = []
+        self.graphs: list = []   # level -> (nbr, moments)
+        self.idx: List[Tensor] = []    # level -> decimation indices into it
+        self.tables: list = []   # level l -> (nbr, dist2) of the l+1 -> l interpolation
+        self.ready: list = []    # level -> torch.cuda.Event (graph of the level complete) or None
+        self.moved: list = []    # level -> torch.cuda.Event (its draw and the next level's positions complete) or None
+        self.done = None
+
+    def _wait(self, ev) -> None:
+        if ev is not None:
+            torch.cuda.current_stream().wait_event(ev)
+
+    def graph_of(self, lvl_idx: int):
+        self._wait(self.ready[lvl_idx])
+        return self.graphs[lvl_idx]
+
+    def after_level(self, lvl_idx: int):
+        """(decimation indices of level ``lvl_idx``, positions of level ``lvl_idx + 1``)."""
+        self._wait(self.moved[lvl_idx])
+        return self.idx[lvl_idx], self.pos[lvl_idx + 1]
+
+    def table_of(self, lvl_idx: int):
+        self._wait(self.done)
+        return self.tables[lvl_idx]
 
 
 class B200RandLANet(nn.Module):
@@ -319,14 +367,50 @@ class B200RandLANet(nn.Module):
             return idx
         return decimation_indices(levels[lvl_idx].ptr_host, self.decimation, levels[lvl_idx].ptr.device)[0]
 
-    def _decimate(self, tensors, levels: List["_Level"], lvl_idx: int):
-        """decimate() of pyg_randla_net.py:234-238 (x rows through the gather kernel; pos rows too)."""
+    def _decimation_idx(self, levels: List["_Level"], lvl_idx: int, device: torch.device) -> Tensor:
+        """decimation_indices() of pyg_randla_net.py:192-231 for one level (or the parity harness's injected ones)."""
         if self.injected_decimation_idx is not None:
-            idx = self.injected_decimation_idx[lvl_idx].to(device=tensors[0].device, dtype=torch.int64)
+            idx = self.injected_decimation_idx[lvl_idx].to(device=device, dtype=torch.int64)
         else:
             idx = self.draw_decimation(levels, lvl_idx)
         self.last_decimation_idx.append(idx)
-        return tuple(ops.gather_rows(t, idx) for t in tensors)
+        return idx
+
+    def _geometry(self, pos: Tensor, levels: List["_Level"]) -> _Geometry:
+        """The position-only half of the forward pass (see :class:`_Geometry`): same calls in the same order as the
+        interleaved reference code (:58-79), so the random stream of the draws is consumed identically."""
+        g = _Geometry()
+        blocks = (self.block1, self.block2, self.block3, self.block4)
+        fork = ops.fork_enabled()
+        if fork:
+            main, side = torch.cuda.current_stream(), ops.side_stream(pos.device)
+            side.wait_stream(main)
+            ctx = torch.cuda.stream(side)
+        else:
+            import contextlib
+            ctx = contextlib.nullcontext()
+
+        def mark():
+            if fork:
+                ev = torch.cuda.Event()
+                ev.record(side)
+                return ev
+            return None
+
+        with ctx:
+            g.pos.append(pos)
+            for l, block in enumerate(blocks):
+                g.graphs.append(block.graph(g.pos[l], levels[l]))  # knn_graph (:180)
+                g.ready.append(mark())
+                idx = self._decimation_idx(levels, l, pos.device)   # decimate (:59-68)
+                g.idx.append(idx)
+                g.pos.append(ops.gather_rows(g.pos[l], idx))
+                g.moved.append(mark())
+            fps = (self.fp1, self.fp2, self.fp3, self.fp4)
+            for l, fp in enumerate(fps):  # level l+1 -> level l (knn_interpolate's search, :248-250)
+                g.tables.append(fp.table(g.pos[l + 1], levels[l + 1], g.pos[l], levels[l]))
+            g.done = mark()
+        return g
 
     def forward(self, x: Optional[Tensor], pos: Tensor, batch: Optional[Tensor], ptr: Tensor) -> Tensor:
         if not pos.is_cuda:
@@ -349,26 +433,31 @@ class B200RandLANet(nn.Module):
             if self.keep_stages:
                 self.stages[name] = t
 
+        geo = self._geometry(pos, levels)
         h0 = ops.linear(x, self.fc0.weight, self.fc0.bias)  # fc0 (:58)
-        b1 = self.block1(h0, pos, lvl0)
+        b1 = self.block1(h0, pos, lvl0, geo, 0)
         keep("b1", b1)
-        b1d, pos1 = self._decimate((b1, pos), levels, 0)  # :59
-        b2 = self.block2(b1d, pos1, lvl1)
+        idx0, pos1 = geo.after_level(0)
+        b1d = ops.gather_rows(b1, idx0)  # decimate (:59)
+        b2 = self.block2(b1d, pos1, lvl1, geo, 1)
         keep("b2", b2)
-        b2d, pos2 = self._decimate((b2, pos1), levels, 1)  # :62
-        b3 = self.block3(b2d, pos2, lvl2)
+        idx1, pos2 = geo.after_level(1)
+        b2d = ops.gather_rows(b2, idx1)  # :62
+        b3 = self.block3(b2d, pos2, lvl2, geo, 2)
         keep("b3", b3)
-        b3d, pos3 = self._decimate((b3, pos2), levels, 2)  # :65
-        b4 = self.block4(b3d, pos3, lvl3)
+        idx2, pos3 = geo.after_level(2)
+        b3d = ops.gather_rows(b3, idx2)  # :65
+        b4 = self.block4(b3d, pos3, lvl3, geo, 3)
         keep("b4", b4)
-        b4d, pos4 = self._decimate((b4, pos3), levels, 3)  # :68
+        idx3, pos4 = geo.after_level(3)
+        b4d = ops.gather_rows(b4, idx3)  # :68
 
         summit = self.mlp_summit(b4d)  # :70
         keep("summit", summit)
-        fp4 = self.fp4(summit, pos4, lvl4, b3d, pos3, lvl3)  # :76
-        fp3 = self.fp3(fp4, pos3, lvl3, b2d, pos2, lvl2)
-        fp2 = self.fp2(fp3, pos2, lvl2, b1d, pos1, lvl1)
-        fp1 = self.fp1(fp2, pos1, lvl1, b1, pos, lvl0)  # :79
+        fp4 = self.fp4(summit, pos4, lvl4, b3d, pos3, lvl3, geo.table_of(3))  # :76
+        fp3 = self.fp3(fp4, pos3, lvl3, b2d, pos2, lvl2, geo.table_of(2))
+        fp2 = self.fp2(fp3, pos2, lvl2, b1d, pos1, lvl1, geo.table_of(1))
+        fp1 = self.fp1(fp2, pos1, lvl1, b1, pos, lvl0, geo.table_of(0))  # :79
         keep("fp1", fp1)
 
         h = self.mlp_classif(fp1)  # :81
