@@ -64,6 +64,7 @@ int launch_tc_nt(const float* a1, int64_t ld1, int c1, const float* a2, int64_t 
                  const float* bias, float* o1, int64_t old1, int oc1, float* o2, int64_t old2, double* colstats, int64_t n,
                  cudaStream_t st);
 int launch_transpose(const float* w, float* wt, int rows, int cols, cudaStream_t st);
+bool tc_path_enabled(int bit);  // runtime.cu: b200_set_option("tensor_core_paths", mask) -- per-kernel-family A/B switch
 bool tensor_cores_enabled();  // runtime.cu: b200_set_option("tensor_cores", 0) selects the FMA kernels (A/B switch)
 
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }

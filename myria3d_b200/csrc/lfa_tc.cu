@@ -402,6 +402,11 @@ lfa_tc_kernel(const float* __restrict__ x, const float* __restrict__ pos, const 
     auto e1_centre = [&](const int g, const int deg, auto full_tag) {
       constexpr bool FULL = decltype(full_tag)::value;
       float a[KT], f[KT];
+      float go_v = 0.f;  // (backward) issued first: its latency hides behind the softmax
+      if constexpr (BWD) {
+        if (tile_base + g < n) go_v = __ldg(grad_out + (tile_base + g) * C + ch);
+      }
+      (void)go_v;
 #pragma unroll
       for (int k0 = 0; k0 < KT; k0 += 16) {
         float v[16];
@@ -453,7 +458,7 @@ lfa_tc_kernel(const float* __restrict__ x, const float* __restrict__ pos, const 
         // softmax gradient then sits in fp16's normal range whatever the loss scale is; undone in E3 / the dW flush
         // dA is stored as kWScale * gscale * dA: the accumulators of MMA3 / MMA4 then carry kWScale^2 * gscale and
         // kWScale * gscale (3 instead of 4 operations per edge here)
-        const float gi = (i < n) ? inv * __ldg(grad_out + i * C + ch) * (gscale * kWScale) : 0.f;
+        const float gi = inv * go_v * (gscale * kWScale);
 #pragma unroll
         for (int k8 = 0; k8 < KT; k8 += 8) {
           float da[8];
@@ -691,7 +696,7 @@ static int launch_lfa_tc(const float* x, const float* pos, const int32_t* nbr, c
 // returns B200_E_UNSUPPORTED when this (c, kt) has no tensor-core kernel (the caller then uses the FMA kernel)
 int lfa_tc_fwd_dispatch(const float* x, const float* pos, const int32_t* nbr, const float* enc_w, const float* enc_b,
                         const float* att_wt, float* out, int64_t n, int c, int kt, cudaStream_t st) {
-  if (!tensor_cores_enabled()) return B200_E_UNSUPPORTED;
+  if (!tc_path_enabled(16)) return B200_E_UNSUPPORTED;
 #define X(C_, KT_, NEF_, NEB_)                                                                                     \
   if (c == C_ && kt == KT_)                                                                                        \
     return launch_lfa_tc<C_, NEF_, KT_, false>(x, pos, nbr, enc_w, enc_b, nullptr, att_wt, out, nullptr, nullptr, nullptr, \
@@ -724,7 +729,7 @@ int lfa_tc_bwd_dispatch(const float* x, const float* pos, const int32_t* nbr, co
 }
 
 bool lfa_tc_supported(int c, int kt) {
-  if (!tensor_cores_enabled()) return false;
+  if (!tc_path_enabled(16)) return false;
 #define X(C_, KT_, NEF_, NEB_) \
   if (c == C_ && kt == KT_) return true;
   B200_LFA_TC_CASES(X)

@@ -486,7 +486,7 @@ static int launch_tn_skinny(const float* gy, int cout, const CatRows& A, float* 
 // generic dispatcher of gw[cout, c1+c2] += gy^T [a1|a2], gb += colsum(gy)
 static bool tn_uses_tensor_cores(const float* gy, int cout, const CatRows& A, const float* gw, int64_t n) {
   return cout >= 64 && A.c1 + A.c2 >= 64 && n >= 512 && cout % 4 == 0 && A.vec && aligned16(gy) && aligned16(gw) &&
-         tensor_cores_enabled();
+         tc_path_enabled(4);
 }
 
 static int launch_tn(const float* gy, int cout, const CatRows& A, float* gw, float* gb, int64_t n, float* ws,
@@ -896,7 +896,7 @@ extern "C" int b200_linear_fwd(const float* a1, int64_t ld1, int32_t c1, const f
   B200_REQUIRE(ld1 >= c1 && (c2 == 0 || ld2 >= c2), B200_E_INVALID, "b200_linear_fwd: row stride < width");
   if (n <= 0) return B200_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (tc_nt_shape_ok(n, c1, c2, cout))  // tcgen05 (3xTF32): every layer with >= 64 input and output channels
+  if (tc_nt_shape_ok(n, c1, c2, cout) && tc_path_enabled(1))  // tcgen05 (3xTF32): every layer with >= 64 input and output channels
     return launch_tc_nt(a1, ld1, c1, a2, ld2, c2, w, cout, bias, y, cout, cout, nullptr, 0, colstats, n, st);
   const CatRows A = make_cat(a1, ld1, c1, a2, ld2, c2);
   const bool wvec = aligned16(w) && ((c1 + c2) % 4 == 0);
@@ -917,7 +917,7 @@ extern "C" int b200_linear_fwd(const float* a1, int64_t ld1, int32_t c1, const f
 // Input gradients go to the tensor cores below level 1 only: on >= 51 200 rows the layers are HBM-bound and the FMA
 // kernel (no transpose pass, no idle TMEM lanes for narrow outputs) is as fast or faster (profiles/).
 static bool bwd_input_uses_tc(int64_t n, int ktot, int cout) {
-  return n >= 1024 && n <= 32768 && tc_nt_shape_ok(n, cout, 0, ktot);
+  return n >= 1024 && n <= 32768 && tc_nt_shape_ok(n, cout, 0, ktot) && tc_path_enabled(2);
 }
 
 extern "C" int64_t b200_linear_bwd_input_workspace_bytes(int64_t n, int32_t c1, int32_t c2, int32_t cout) {
@@ -977,7 +977,7 @@ extern "C" int b200_linear_bwd_weight(const float* grad_y, const float* a1, int6
 
 extern "C" int64_t b200_linear_fwd_num_stat_partials(int64_t n, int32_t c1, int32_t c2, int32_t cout) {
   if (n <= 0) return 0;
-  if (tc_nt_shape_ok(n, c1, c2, cout)) return ceil_div(n, tc_nt_rows_per_tile(n, cout));
+  if (tc_nt_shape_ok(n, c1, c2, cout) && tc_path_enabled(1)) return ceil_div(n, tc_nt_rows_per_tile(n, cout));
   if (cout <= 32) return ceil_div(n, 128);
   if (cout >= 128 && c1 + c2 >= 64 && ceil_div(n, 128) * ceil_div(cout, 128) >= num_sms()) return ceil_div(n, 128);
   return ceil_div(n, 64);

@@ -26,8 +26,12 @@ void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 // process-wide options (b200_set_option): the only mutable global state besides the launch counter
 static std::atomic<int> g_tensor_cores{1};
+static std::atomic<int> g_tc_paths{0x1f};  // bit 0 linear forward, 1 linear input gradient, 2 wide weight gradient, 3 narrow weight gradient, 4 LFA
 static std::atomic<long long*> g_tc_timeline{nullptr};
 bool tensor_cores_enabled() { return g_tensor_cores.load(std::memory_order_relaxed) != 0; }
+bool tc_path_enabled(int bit) {
+  return tensor_cores_enabled() && (g_tc_paths.load(std::memory_order_relaxed) & bit) != 0;
+}
 long long* tc_debug_buffer() { return g_tc_timeline.load(std::memory_order_relaxed); }
 
 int num_sms() {
@@ -59,16 +63,21 @@ int b200_set_option(const char* key, int64_t value) {
     b200::g_tensor_cores.store(value != 0, std::memory_order_relaxed);
     return B200_OK;
   }
+  if (strcmp(key, "tensor_core_paths") == 0) {
+    b200::g_tc_paths.store((int)value, std::memory_order_relaxed);
+    return B200_OK;
+  }
   if (strcmp(key, "tc_timeline") == 0) {
     b200::g_tc_timeline.store(reinterpret_cast<long long*>(static_cast<intptr_t>(value)), std::memory_order_relaxed);
     return B200_OK;
   }
-  b200::set_error("b200_set_option: unknown option '%s' (known: tensor_cores, tc_timeline)", key);
+  b200::set_error("b200_set_option: unknown option '%s' (known: tensor_cores, tensor_core_paths, tc_timeline)", key);
   return B200_E_INVALID;
 }
 
 int64_t b200_get_option(const char* key) {
   if (key && strcmp(key, "tensor_cores") == 0) return b200::g_tensor_cores.load(std::memory_order_relaxed);
+  if (key && strcmp(key, "tensor_core_paths") == 0) return b200::g_tc_paths.load(std::memory_order_relaxed);
   if (key && strcmp(key, "tc_timeline") == 0)
     return static_cast<int64_t>(reinterpret_cast<intptr_t>(b200::g_tc_timeline.load(std::memory_order_relaxed)));
   return -1;

@@ -235,7 +235,7 @@ static int launch_tsk(const TskArgs& base, cudaStream_t st) {
 }
 
 bool tc_skinny_tn_ok(int cout, int ktot, bool has_bias, int64_t n) {
-  return tensor_cores_enabled() && cout >= 1 && cout <= 64 && ktot >= 1 && ktot + (has_bias ? 1 : 0) <= 64 && n >= 4096 &&
+  return tc_path_enabled(8) && cout >= 1 && cout <= 64 && ktot >= 1 && ktot + (has_bias ? 1 : 0) <= 64 && n >= 4096 &&
          !(cout > 32 && ktot + (has_bias ? 1 : 0) > 32);  // (64 x 64 would need 200 KB of stages: tc_tn_kernel's job)
 }
 

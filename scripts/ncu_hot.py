@@ -1,7 +1,8 @@
 """Summarise an .ncu-rep: headline metrics + hottest SASS instructions with their dominant stall reasons."""
 import csv, subprocess, sys, io
 rep = sys.argv[1]
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+sel = ["--launch-skip", sys.argv[3], "--launch-count", "1"] if len(sys.argv) > 3 else []  # which launch of the report
+raw = subprocess.run(["ncu", "-i", rep] + sel + ["--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, unit, vals = rows[0], rows[1], rows[2]
 want = ["gpu__time_duration.sum", "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
@@ -12,12 +13,12 @@ want = ["gpu__time_duration.sum", "sm__warps_active.avg.pct_of_peak_sustained_ac
         "lts__t_bytes.sum", "l1tex__t_bytes.sum", "smsp__thread_inst_executed_per_inst_executed.ratio"]
 for h, u, v in zip(hdr, unit, vals):
     if h in want: print(f"{h:75s} {v} {u}")
-src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+src = subprocess.run(["ncu", "-i", rep] + sel + ["--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
 hdr = rows[1]
 ci, cs = hdr.index("Source"), hdr.index("# Samples")
 stall = [i for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
-data = [(int(r[cs]), r) for r in rows[2:] if r[cs].isdigit()]
+data = [(int(r[cs]), r) for r in rows[2:] if len(r) > cs and r[cs].isdigit()]
 tot = sum(d[0] for d in data)
 agg = {hdr[i]: sum(int(r[i]) for _, r in data) for i in stall}
 print("stall totals:", sorted(agg.items(), key=lambda x: -x[1])[:7])
