@@ -21,6 +21,8 @@ are one-off layouts and simply take the eager path.  Layouts are identified by t
 """
 from __future__ import annotations
 
+import os
+
 from collections import OrderedDict
 from typing import Dict, List, Optional, Tuple
 
@@ -69,6 +71,11 @@ class GraphedTrainStep:
         self.device = next(model.parameters()).device
         self._captured: "OrderedDict[Tuple[int, ...], _Captured]" = OrderedDict()
         self.library_launches = 0  # kernels of libb200randla replayed so far
+        # N > 1, opt-in (B200_COLLECTIVES_IN_GRAPH=1): capture the NCCL collectives with the step -- one graph, the
+        # BatchNorm-statistics broadcast hidden behind the backward.  Measured on 2 x B200: 6.43 ms/step against 6.44 for
+        # the default graph | eager all-reduce | graph (the cost is the collective itself, not the host gaps), same
+        # losses, and one of three runs did not shut down cleanly -- hence off by default.
+        self.collectives_in_graph = os.environ.get("B200_COLLECTIVES_IN_GRAPH", "0") == "1"
 
     # ------------------------------------------------------------------ helpers
     def _zero_grad(self):
@@ -161,15 +168,28 @@ class GraphedTrainStep:
             mode = "thread_local" if multi else "global"
             cap.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(cap.graph, capture_error_mode=mode):
-                out = self._fwd_bwd(cap)
-                if not multi:
+                if multi and self.collectives_in_graph:
+                    # ONE graph per step, collectives included: rank 0's BatchNorm statistics travel while the
+                    # backward runs (they are final once the forward is done; torch DDP sends them before the NEXT
+                    # forward -- same values), the flat gradient all-reduce follows the last backward kernel
+                    self._zero_grad()
+                    out = self.model.training_step(Batch(**cap.static), 0)
+                    bcast = self.reducer.start_broadcast()
+                    out["loss"].backward()
+                    red = self.reducer.all_reduce(async_op=True)
+                    self.reducer.finish_broadcast(bcast)
+                    red.wait()
                     self.optimizer.step()
+                else:
+                    out = self._fwd_bwd(cap)
+                    if not multi:
+                        self.optimizer.step()
                 cap.loss = out["loss"].detach()
                 cap.logits = out["logits"].detach()
                 if cap.draws_in_graph:  # the subsets of the last replay (static tensors owned by the graph)
                     cap.idx_static = list(self.net.last_decimation_idx)
             cap.launches_per_step = _lib.launch_count() - n0
-            if multi:
+            if multi and not self.collectives_in_graph:
                 cap.opt_graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(cap.opt_graph, capture_error_mode=mode):
                     self.optimizer.step()
@@ -206,9 +226,9 @@ class GraphedTrainStep:
     def __call__(self, batch) -> Tensor:
         key = self._layout_key(batch)
         multi = self.reducer is not None and self.reducer.world_size > 1
-        if multi:
-            self.reducer.broadcast_buffers()  # torch DDP's broadcast_buffers=True (rank 0's BatchNorm statistics)
         cap = self._captured.get(key)
+        if multi and not (self.collectives_in_graph and cap is not None):
+            self.reducer.broadcast_buffers()  # torch DDP's broadcast_buffers=True (rank 0's BatchNorm statistics)
         if cap is None:
             n_seen = self._seen.get(key, 0)
             if n_seen < self.capture_after:

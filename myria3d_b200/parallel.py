@@ -72,25 +72,40 @@ class FlatGradAllReducer:
     def zero_grad(self) -> None:
         self.flat.zero_()
 
+    def _buffer_views(self):
+        if self._buffers is None:
+            self._buffers = [b for b in self._module.buffers() if b.is_floating_point()]
+            self._flat_buffers = torch.empty(sum(b.numel() for b in self._buffers), dtype=torch.float32,
+                                             device=self.flat.device)
+        return ([b.reshape(-1) for b in self._buffers],
+                list(self._flat_buffers.split([b.numel() for b in self._buffers])))
+
     def broadcast_buffers(self, src: int = 0) -> None:
         """torch DDP's default ``broadcast_buffers=True``: before every forward, rank ``src``'s floating buffers (the
         BatchNorm running statistics: 8 179 floats) replace everybody else's, so that every rank checkpoints the
         same state (the reference trains with Lightning's stock DDP,
         configs/experiment/RandLaNet_base_run_FR-MultiGPU.yaml:9-13).  One flat broadcast per call; a no-op on one
         rank.  ``num_batches_tracked`` counters advance identically on every rank and are left alone."""
+        self.finish_broadcast(self.start_broadcast(src))
+
+    def start_broadcast(self, src: int = 0):
+        """First half of :meth:`broadcast_buffers`: pack + asynchronous broadcast.  Returns a handle for
+        :meth:`finish_broadcast` (None on one rank).  GraphedTrainStep issues it right after the forward pass -- the
+        running statistics do not change again until the next forward -- so the transfer hides behind the backward."""
         if self.world_size == 1:
+            return None
+        bufs, parts = self._buffer_views()
+        if not bufs:
+            return None
+        torch._foreach_copy_(parts, bufs)
+        return dist.broadcast(self._flat_buffers, src=src, group=self.group, async_op=True)
+
+    def finish_broadcast(self, work) -> None:
+        if work is None:
             return
-        if self._buffers is None:
-            self._buffers = [b for b in self._module.buffers() if b.is_floating_point()]
-            self._flat_buffers = torch.empty(sum(b.numel() for b in self._buffers), dtype=torch.float32,
-                                             device=self.flat.device)
-        if not self._buffers:
-            return
-        torch._foreach_copy_(list(self._flat_buffers.split([b.numel() for b in self._buffers])),
-                             [b.reshape(-1) for b in self._buffers])
-        dist.broadcast(self._flat_buffers, src=src, group=self.group)
-        torch._foreach_copy_([b.reshape(-1) for b in self._buffers],
-                             list(self._flat_buffers.split([b.numel() for b in self._buffers])))
+        work.wait()
+        bufs, parts = self._buffer_views()
+        torch._foreach_copy_(bufs, parts)
 
 
 def shard_tiles(num_tiles: int, rank: int, world_size: int) -> List[int]:
