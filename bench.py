@@ -213,7 +213,10 @@ def algorithmic_flops(name: str, a):
 def ncu_traffic(name: str, a):
     """dram bytes per launch of this kernel/shape from the committed single-kernel ncu capture, else None."""
     try:
-        with open(os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")) as f:
+        path = os.path.join(ROOT, "profiles", "ncu_traffic_r02.json")
+        if not os.path.exists(path):
+            path = os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")
+        with open(path) as f:
             entries = json.load(f)["entries"]
     except Exception:
         return None, None
@@ -677,7 +680,12 @@ def run_b200(args):
                                  "frac": tfs / fma_peak if fma_peak else None},
                     "peak_source": peak_src, "launch_ms": top["ms_per_launch"],
                     "share_of_library_time": top["ms"] / lib_ms if lib_ms > 0 else None,
-                    "library_ms_per_step": lib_ms}
+                    "library_ms_per_step": lib_ms,
+                    # the next library calls by time, same definition of `achieved` (algorithmic bytes / CUDA-event time)
+                    "also": [{"kernel": g["name"], "kernel_args": g["args"], "launch_ms": g["ms_per_launch"],
+                              "achieved": g["gbs"], "frac": g["gbs"] / peak,
+                              "traffic": ncu_traffic(g["name"], tuple(g["args"]))[0]}
+                             for g in table[1:9] if g["alg_bytes"] > 0]}
             report = args.kernel_report
             if report is None and os.path.isdir(os.path.join(ROOT, "gpurun_out")):
                 report = os.path.join(ROOT, "gpurun_out", "bench_kernels.json")

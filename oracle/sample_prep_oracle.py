@@ -53,3 +53,26 @@ def grid_sampling(pos: torch.Tensor, x: torch.Tensor, y: torch.Tensor, size: flo
 
 def center(pos: torch.Tensor) -> torch.Tensor:
     return pos - pos.mean(dim=-2, keepdim=True)
+
+
+def maximum_num_nodes(n: int, num: int):
+    """``MaximumNumNodes.__call__`` (myria3d/pctl/transforms/transforms.py:48-61): None when ``n <= num``, else the row
+    choice ``torch.randperm(n)[:num]`` (global CPU generator, like the reference)."""
+    if n <= num:
+        return None
+    return torch.randperm(n)[:num]
+
+
+def minimum_num_nodes(n: int, num: int):
+    """``MinimumNumNodes.__call__`` (transforms.py:64-81): None when ``n >= num``, else whole random permutations
+    repeated ``ceil(num / n)`` times, cut at ``num``."""
+    import math
+
+    if n >= num:
+        return None
+    return torch.cat([torch.randperm(n) for _ in range(math.ceil(num / n))], dim=0)[:num]
+
+
+def normalize_pos(pos: torch.Tensor, subtile_width: float = 50) -> torch.Tensor:
+    """``NormalizePos`` (transforms.py:149-162): xy to [-1, 1] by scaling the whole cloud with 1 / (subtile_width / 2)."""
+    return pos * (1 / (subtile_width / 2))

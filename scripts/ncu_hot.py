@@ -18,7 +18,11 @@ rows = list(csv.reader(io.StringIO(src)))
 hdr = rows[1]
 ci, cs = hdr.index("Source"), hdr.index("# Samples")
 stall = [i for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
-data = [(int(r[cs]), r) for r in rows[2:] if len(r) > cs and r[cs].isdigit()]
+data, seen = [], set()
+for r in rows[2:]:  # (the source page repeats every SASS row once per view: keep one)
+    if len(r) > cs and r[cs].isdigit() and tuple(r) not in seen:
+        seen.add(tuple(r))
+        data.append((int(r[cs]), r))
 tot = sum(d[0] for d in data)
 agg = {hdr[i]: sum(int(r[i]) for _, r in data) for i in stall}
 print("stall totals:", sorted(agg.items(), key=lambda x: -x[1])[:7])

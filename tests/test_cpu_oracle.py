@@ -244,3 +244,50 @@ def test_sample_prep_oracle_pins():
     p = torch.tensor([[0.0, 0.0, 0.0], [0.1, 0.1, 0.1], [0.3, 0.0, 0.0], [1.0, 1.0, 1.0]])
     po, xo, yo, uniq = SO.grid_sampling(p, p.clone(), torch.tensor([2, 1, 0, 1]), 0.25)
     assert po.shape[0] == 3 and torch.allclose(po[0], torch.tensor([0.05, 0.05, 0.05])) and yo.tolist() == [1, 0, 1]
+
+
+def test_sample_prep_oracle_against_reference_run_vectors():
+    """PINNED: tests/golden/ref_sample_prep.npz holds outputs of the reference's OWN functions (oracle/gen_golden_ref.py
+    loads pctl/dataset/utils.py and pctl/transforms/transforms.py from /root/reference and runs them on seeded inputs).
+    The restatement must reproduce them exactly: receptive-field index sets (incl. points on field borders), mosaic
+    centres, the node-budget draws under the same torch seed, NormalizePos."""
+    import os
+    from oracle import sample_prep_oracle as SO
+
+    ref = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_sample_prep.npz"))
+    assert ref["mosaic_counts"].tolist() == [400, 1521]
+    for tag in "abc":
+        tile, sub, ov = ref[f"split_{tag}_args"].tolist()
+        fields = SO.split_cloud_into_samples(ref[f"split_{tag}_pos"], tile, sub, ov)
+        off = ref[f"split_{tag}_off"]
+        assert len(fields) == len(off) - 1
+        assert np.array_equal(np.concatenate(fields), ref[f"split_{tag}_idx"])
+        assert [len(f) for f in fields] == np.diff(off).tolist()
+        assert np.array_equal(np.stack(SO.get_mosaic_of_centers(tile, sub, ov)), ref[f"split_{tag}_centers"])
+    torch.manual_seed(2024)  # the generator's sequence: pos, x, then the transform's randperm
+    pos, x = torch.rand(500, 3) * 50.0 - 25.0, torch.rand(500, 4)
+    assert np.array_equal(pos.numpy(), ref["max_pos_in"]) and np.array_equal(x.numpy(), ref["max_x_in"])
+    choice = SO.maximum_num_nodes(500, 200)
+    assert np.array_equal(pos[choice].numpy(), ref["max_pos_out"]) and np.array_equal(x[choice].numpy(), ref["max_x_out"])
+    assert int(ref["max_num_nodes"]) == 200 and SO.maximum_num_nodes(150, 200) is None
+    torch.manual_seed(2025)
+    choice = SO.minimum_num_nodes(70, 300)
+    assert np.array_equal(pos[:70][choice].numpy(), ref["min_pos_out"]) and int(ref["min_num_nodes"]) == 300
+    assert SO.minimum_num_nodes(300, 300) is None
+    assert np.array_equal(SO.normalize_pos(pos, 50).numpy(), ref["normalize_pos_out"])
+
+
+def test_stitch_oracle_against_reference_run_vectors():
+    """PINNED (as far as torch_scatter's absence allows): the reference's Interpolator.store_predictions +
+    reduce_predicted_logits (myria3d/models/interpolation.py:94-121), run by oracle/gen_golden_ref.py with scatter_sum
+    supplied as index_add_ (torch_scatter's CPU order), against the oracle's restatement: bit-exact, incl. the duplicated
+    rows of `reduced_logits[idx_in_full_cloud]`."""
+    import os
+    from oracle import stitch_oracle as SO
+
+    ref = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_sample_prep.npz"))
+    logits, idx = torch.from_numpy(ref["stitch_logits"]), ref["stitch_idx"]
+    red, idx_out = SO.reduce_predicted_logits([logits[:1400], logits[1400:2800], logits[2800:]],
+                                              [idx[:1400], idx[1400:2800], idx[2800:]], int(ref["stitch_nb_points"]))
+    assert np.array_equal(idx_out, ref["stitch_idx_out"])
+    assert np.array_equal(red.numpy(), ref["stitch_reduced"])

@@ -35,6 +35,36 @@ def test_split_cloud_into_samples_bit_exact(lib, tile, sub, overlap, n):
         assert len(SO.get_mosaic_of_centers(1000, 50, 0)) == 400 and len(SO.get_mosaic_of_centers(1000, 50, 25)) == 1521
 
 
+def test_split_against_reference_run_vectors(lib):
+    """The CUDA receptive-field split against index sets produced by the REFERENCE'S OWN split_cloud_into_samples
+    (tests/golden/ref_sample_prep.npz, written by oracle/gen_golden_ref.py from /root/reference): bit-exact."""
+    import os
+    from myria3d_b200.sample_prep import split_cloud_into_samples, maximum_num_nodes, minimum_num_nodes
+
+    ref = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_sample_prep.npz"))
+    for tag in "abc":
+        tile, sub, ov = ref[f"split_{tag}_args"].tolist()
+        got = split_cloud_into_samples(torch.from_numpy(ref[f"split_{tag}_pos"]).to(DEV), tile, sub, ov)
+        off = ref[f"split_{tag}_off"]
+        assert len(got) == len(off) - 1
+        assert np.array_equal(torch.cat(got).cpu().numpy(), ref[f"split_{tag}_idx"])
+        assert [int(t.numel()) for t in got] == np.diff(off).tolist()
+    # node budgets: the random stream is the library's own (Philox), so the draw is compared as a distribution-free
+    # property -- exactly what the reference's outputs satisfy too: `num` rows, each an input row; no repeats when
+    # sub-sampling, every row at least floor(num / n) times when padding
+    rows = {tuple(r) for r in ref["max_pos_in"].tolist()}
+    assert len({tuple(r) for r in ref["max_pos_out"].tolist()}) == 200 and {tuple(r) for r in ref["max_pos_out"].tolist()} <= rows
+    choice = maximum_num_nodes(500, 200, DEV, seed=5)
+    assert choice.numel() == 200 and choice.unique().numel() == 200 and int(choice.min()) >= 0 and int(choice.max()) < 500
+    choice = minimum_num_nodes(70, 300, DEV, seed=5)
+    counts = torch.bincount(choice, minlength=70)
+    assert choice.numel() == 300 and int(counts.min()) >= 4 and int(counts.max()) <= 5  # 300 = 4 * 70 + 20
+    ref_counts = {}
+    for r in ref["min_pos_out"].tolist():
+        ref_counts[tuple(r)] = ref_counts.get(tuple(r), 0) + 1
+    assert len(ref_counts) == 70 and min(ref_counts.values()) >= 4 and max(ref_counts.values()) <= 5
+
+
 def test_segmented_sort_pairs(lib):
     from ctypes import c_void_p
 

@@ -38,6 +38,18 @@ def test_scatter_sum_is_bit_identical_to_the_cpu_scatter(nb_points, n_windows, s
         assert torch.equal(want, SO.scatter_sum_rows_loop(logits, idx.tolist(), nb_points))
 
 
+def test_scatter_sum_against_reference_run_vectors():
+    """CUDA scatter-sum + gather against the output of the REFERENCE'S OWN Interpolator.reduce_predicted_logits
+    (tests/golden/ref_sample_prep.npz, oracle/gen_golden_ref.py): bit-exact."""
+    import os
+    from myria3d_b200 import ops
+
+    ref = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_sample_prep.npz"))
+    logits, idx = torch.from_numpy(ref["stitch_logits"]).to(DEV), torch.from_numpy(ref["stitch_idx"]).to(DEV)
+    summed = ops.stitch_scatter_sum(logits, idx, int(ref["stitch_nb_points"]))
+    assert np.array_equal(summed[idx].cpu().numpy(), ref["stitch_reduced"])
+
+
 def test_scatter_sum_odd_class_count_and_errors():
     from myria3d_b200 import ops
 
