@@ -181,6 +181,9 @@ def test_oracle_matches_trained_checkpoint_golden():
     with torch.no_grad():
         logits = net(x, pos, batch, ptr, decimation_idx=g["decimation_idx"])
     assert_close(logits, g["logits_fp32"], atol=2e-5, what="oracle logits vs trained-checkpoint golden")
+    # ... and those logits are what the reference's OWN model file (executed on stand-in PyG primitives with these shipped
+    # weights, oracle/gen_golden_ckpt.py) produced, bit for bit
+    assert g["reference_model_code_equals_oracle"] and torch.equal(g["logits_reference_model_code"], g["logits_fp32"])
     assert_close(logits, g["logits_fp64"], atol=1e-4 + 10 * g["fp32_vs_fp64_max_err"], what="fp32 oracle vs fp64 oracle")
     assert float(g["logits_fp32"].abs().max()) > 10.0  # realistic magnitudes, unlike the random-init fixtures
 
@@ -291,3 +294,29 @@ def test_stitch_oracle_against_reference_run_vectors():
                                               [idx[:1400], idx[1400:2800], idx[2800:]], int(ref["stitch_nb_points"]))
     assert np.array_equal(idx_out, ref["stitch_idx_out"])
     assert np.array_equal(red.numpy(), ref["stitch_reduced"])
+
+
+def test_oracle_equals_reference_model_code():
+    """PINNED: tests/golden/ref_model_standin.pt was produced by executing the reference's OWN model file
+    (myria3d/models/modules/pyg_randla_net.py, unmodified) on stand-ins for the uninstallable PyG primitives
+    (oracle/pyg_standin.py, oracle/gen_golden_ref_model.py).  The oracle restatement, run on the same seeds, must give
+    bit-identical eval logits, train logits, loss, parameter gradients and BatchNorm buffers -- i.e. the same wiring,
+    operator order, state-dict names and random-stream consumption (per-cloud randperm, dropout) as the reference file.
+    Both kNN back-ends of the oracle (kd-tree like torch_cluster's CPU path, brute force) are held to it."""
+    import os
+    from oracle import gen_golden_ref_model as G
+
+    gold = torch.load(os.path.join(os.path.dirname(__file__), "golden", "ref_model_standin.pt"))
+    for name, c in gold["cases"].items():
+        for method in ("kdtree", "brute"):
+            out = G.run_case(lambda k: O.OracleRandLANet(9, 6, decimation=4, num_neighbors=k, return_logits=True,
+                                                         knn_method=method), **c)
+            g = gold[name]
+            assert torch.equal(out["eval_logits"], g["eval_logits"]), (name, method)
+            assert torch.equal(out["train_logits"], g["train_logits"]) and torch.equal(out["loss"], g["loss"])
+            for n, v in g["grads_full"].items():
+                assert torch.equal(out["grads"][n], v), n
+            for n, v in g["grad_norms"].items():
+                assert float(out["grads"][n].double().norm()) == float(v), n
+            for n, v in g["buffers"].items():
+                assert torch.equal(out["buffers"][n], v), n

@@ -346,3 +346,38 @@ def test_config_a_block1_net_parity(lib):
     with torch.no_grad():
         assert_close(net(x.to(DEV), pos.to(DEV), batch.to(DEV), ptr.to(DEV)), ref(x, pos, batch, ptr), atol=LOGIT_TOL,
                      what="config A eval logits")
+
+
+def test_eval_logits_against_reference_model_code_vectors(lib):
+    """CUDA eval forward against logits computed by the reference's OWN model file on stand-in PyG primitives
+    (tests/golden/ref_model_standin.pt; oracle/gen_golden_ref_model.py).  The decimation subsets are the reference's
+    randperm draws, recovered by re-running the (bit-identical, see test_oracle_equals_reference_model_code) oracle
+    on the same seed."""
+    import os
+    from myria3d_b200 import B200RandLANet
+
+    gold = torch.load(os.path.join(os.path.dirname(__file__), "golden", "ref_model_standin.pt"))
+    for name, c in gold["cases"].items():
+        sizes, k, seed = c["sizes"], c["k"], c["seed"]
+        torch.manual_seed(seed)
+        ref = O.OracleRandLANet(9, 6, num_neighbors=k, return_logits=True)
+        g = torch.Generator().manual_seed(seed + 1)
+        for m in ref.modules():
+            if isinstance(m, torch.nn.BatchNorm1d):
+                m.weight.data.uniform_(0.7, 1.3, generator=g)
+                m.bias.data.uniform_(-0.2, 0.2, generator=g)
+                m.running_mean.uniform_(-0.2, 0.2, generator=g)
+                m.running_var.uniform_(0.6, 1.4, generator=g)
+        x, pos, y, batch, ptr = O.synthetic_batch(sizes, seed=seed)
+        ref.eval()
+        torch.manual_seed(seed + 2)
+        with torch.no_grad():
+            lr = ref(x, pos, batch, ptr)
+        assert torch.equal(lr, gold[name]["eval_logits"])  # the oracle run IS the reference run
+        net = B200RandLANet(9, 6, num_neighbors=k, return_logits=True)
+        net.load_state_dict(ref.state_dict(), strict=True)
+        net = net.to(DEV).eval()
+        net.injected_decimation_idx = ref.last_decimation_idx
+        with torch.no_grad():
+            lg = net(x.to(DEV), pos.to(DEV), batch.to(DEV), ptr.to(DEV))
+        assert_close(lg, gold[name]["eval_logits"], atol=LOGIT_TOL, what=f"eval logits vs reference model code ({name})")
