@@ -45,6 +45,9 @@ int b200_check_device(void);
  * the only mutable global state; compute entry points are otherwise pure functions of their arguments.
  *   "tensor_cores"  1 (default) / 0: A/B switch that routes every tcgen05 kernel to its fp32-FMA counterpart
  *                   (tests and profiles compare the two; no reference counterpart).
+ *   "tensor_core_paths"  bitmask (default 31) of the kernel families allowed on the tensor cores while "tensor_cores" is 1:
+ *                   1 Linear forward, 2 Linear input gradient, 4 wide weight gradient, 8 narrow weight gradient,
+ *                   16 fused LFA forward/backward.  Used to attribute numerical differences to one family.
  *   "tc_timeline"   device pointer (as integer) to 128 int64 receiving clock64() marks of CTA 0 of the tcgen05 GEMMs
  *                   (scripts/tc_timeline.py); 0 (default) = off.
  * b200_get_option returns the current value, -1 for an unknown key. */
