@@ -64,6 +64,12 @@ int launch_tc_nt(const float* a1, int64_t ld1, int c1, const float* a2, int64_t 
                  const float* bias, float* o1, int64_t old1, int oc1, float* o2, int64_t old2, double* colstats, int64_t n,
                  cudaStream_t st);
 int launch_transpose(const float* w, float* wt, int rows, int cols, cudaStream_t st);
+// linear_rows.cu: one thread per row, narrow layers of levels 0-1
+bool linear_rows_ok(int64_t n, int k, int co);
+int linear_rows_grid(int64_t n);
+int launch_linear_rows(const float* a1, int64_t ld1, int c1, const float* a2, int64_t ld2, int c2, const float* w, int w_ld,
+                       bool w_out_major, const float* bias, float* o1, int64_t old1, int oc1, float* o2, int64_t old2, int oc2,
+                       int64_t n, double* colstats, cudaStream_t st);
 bool tc_path_enabled(int bit);  // runtime.cu: b200_set_option("tensor_core_paths", mask) -- per-kernel-family A/B switch
 bool tensor_cores_enabled();  // runtime.cu: b200_set_option("tensor_cores", 0) selects the FMA kernels (A/B switch)
 

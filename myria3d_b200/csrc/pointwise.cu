@@ -898,6 +898,8 @@ extern "C" int b200_linear_fwd(const float* a1, int64_t ld1, int32_t c1, const f
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (tc_nt_shape_ok(n, c1, c2, cout) && tc_path_enabled(1))  // tcgen05 (3xTF32): every layer with >= 64 input and output channels
     return launch_tc_nt(a1, ld1, c1, a2, ld2, c2, w, cout, bias, y, cout, cout, nullptr, 0, colstats, n, st);
+  if (linear_rows_ok(n, c1 + c2, cout))  // narrow layers of levels 0-1: one thread per row (linear_rows.cu)
+    return launch_linear_rows(a1, ld1, c1, a2, ld2, c2, w, c1 + c2, true, bias, y, cout, cout, nullptr, 0, 0, n, colstats, st);
   const CatRows A = make_cat(a1, ld1, c1, a2, ld2, c2);
   const bool wvec = aligned16(w) && ((c1 + c2) % 4 == 0);
   if (cout <= 32) {
@@ -940,6 +942,9 @@ extern "C" int b200_linear_bwd_input(const float* grad_y, const float* w, float*
     if (rc != B200_OK) return rc;
     return launch_tc_nt(grad_y, cout, cout, nullptr, 0, 0, wt, ktot, nullptr, ga1, ldg1, c1, ga2, ldg2, nullptr, n, st);
   }
+  if (linear_rows_ok(n, cout, ktot))  // narrow layers of levels 0-1: the row-streaming kernel with W read as [cout][ktot]
+    return launch_linear_rows(grad_y, cout, cout, nullptr, 0, 0, w, ktot, false, nullptr, ga1, ldg1, c1, ga2, ldg2, c2, n,
+                              nullptr, st);
   const bool gvec = aligned16(grad_y) && (cout % 4 == 0);
   const bool wvec = aligned16(w) && (ktot % 4 == 0);
   if (ktot <= 32) {
@@ -978,6 +983,7 @@ extern "C" int b200_linear_bwd_weight(const float* grad_y, const float* a1, int6
 extern "C" int64_t b200_linear_fwd_num_stat_partials(int64_t n, int32_t c1, int32_t c2, int32_t cout) {
   if (n <= 0) return 0;
   if (tc_nt_shape_ok(n, c1, c2, cout) && tc_path_enabled(1)) return ceil_div(n, tc_nt_rows_per_tile(n, cout));
+  if (linear_rows_ok(n, c1 + c2, cout)) return linear_rows_grid(n);
   if (cout <= 32) return ceil_div(n, 128);
   if (cout >= 128 && c1 + c2 >= 64 && ceil_div(n, 128) * ceil_div(cout, 128) >= num_sms()) return ceil_div(n, 128);
   return ceil_div(n, 64);

@@ -330,6 +330,44 @@ def test_linear_weight_grad_tensor_cores(lib, n, c1, c2, cout):
     assert rel_err(ag[2].grad, gb_ref) < 5e-6, rel_err(ag[2].grad, gb_ref)
 
 
+@pytest.mark.parametrize("n,c1,c2,cout", [(204800, 32, 0, 32), (60001, 9, 0, 32), (8192, 32, 32, 32), (20000, 17, 0, 6),
+                                          (51200, 32, 0, 4), (30000, 64, 0, 32), (10000, 8, 0, 8), (9000, 16, 0, 16),
+                                          (12345, 24, 8, 20), (8200, 16, 48, 5), (40000, 32, 0, 33)])
+def test_linear_row_streaming_kernel(lib, n, c1, c2, cout):
+    """linear_rows.cu (one thread per row; levels 0-1, <= 64 channels on both sides): output, fp64 BatchNorm column
+    statistics (with a large common offset: var = E[y^2] - E[y]^2 must not cancel), input gradients of both segments,
+    vs fp64; vectorised and scalar load / store paths, ragged last tile, padded K and cout."""
+    from myria3d_b200 import ops
+
+    g = torch.Generator().manual_seed(n + cout)
+    a1 = torch.randn(n, c1, generator=g)
+    a2 = torch.randn(n, c2, generator=g) if c2 else None
+    w = torch.randn(cout, c1 + c2, generator=g) / (c1 + c2) ** 0.5
+    b = torch.randn(cout, generator=g) + 30.0  # |mean| >> std
+    gy = torch.randn(n, cout, generator=g)
+    inp = (torch.cat([a1, a2], 1) if c2 else a1).double()
+    y_ref = inp @ w.double().t() + b.double()
+    ga_ref = gy.double() @ w.double()
+    ag = [t.to(DEV).requires_grad_(True) for t in (a1, w, b)] + ([a2.to(DEV).requires_grad_(True)] if c2 else [])
+    y, stats = ops.linear(ag[0], ag[1], ag[2], a2=ag[3] if c2 else None, want_stats=True)
+    y.backward(gy.to(DEV))
+    assert_close(y, y_ref, atol=2e-5, rtol=2e-6, what="linear_rows y")
+    st = stats.sum(0)
+    ycpu = y.detach().double().cpu()
+    mean = st[:cout] / n
+    var = st[cout:] / n - mean * mean
+    assert_close(mean, ycpu.mean(0), atol=0.0, rtol=1e-9, what="column means")
+    assert_close(var, ycpu.var(0, unbiased=False), atol=0.0, rtol=1e-6, what="column variances")
+    assert rel_err(ag[0].grad, ga_ref[:, :c1]) < 2e-6, rel_err(ag[0].grad, ga_ref[:, :c1])
+    if c2:
+        assert rel_err(ag[3].grad, ga_ref[:, c1:]) < 2e-6
+    # only one of the two input gradients wanted (the other output pointer is null)
+    if c2:
+        a1n, a2g = a1.to(DEV), a2.to(DEV).requires_grad_(True)
+        ops.linear(a1n, ag[1].detach(), ag[2].detach(), a2=a2g).backward(gy.to(DEV))
+        assert rel_err(a2g.grad, ga_ref[:, c1:]) < 2e-6
+
+
 @pytest.mark.parametrize("n,c1,c2,cout,bias", [(204800, 32, 0, 4, True), (204800, 9, 0, 32, True), (204800, 32, 0, 33, True),
                                                (51200, 32, 0, 4, True), (60001, 17, 0, 32, True), (4096, 64, 0, 12, False),
                                                (204800, 32, 0, 64, True), (7777, 24, 8, 20, True)])

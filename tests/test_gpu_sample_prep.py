@@ -44,7 +44,7 @@ def test_split_against_reference_run_vectors(lib):
     ref = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_sample_prep.npz"))
     for tag in "abc":
         tile, sub, ov = ref[f"split_{tag}_args"].tolist()
-        got = split_cloud_into_samples(torch.from_numpy(ref[f"split_{tag}_pos"]).to(DEV), tile, sub, ov)
+        got = list(split_cloud_into_samples(torch.from_numpy(ref[f"split_{tag}_pos"]).to(DEV), tile, sub, ov))
         off = ref[f"split_{tag}_off"]
         assert len(got) == len(off) - 1
         assert np.array_equal(torch.cat(got).cpu().numpy(), ref[f"split_{tag}_idx"])
