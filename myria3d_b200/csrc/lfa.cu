@@ -169,28 +169,68 @@ __device__ __forceinline__ void red_vec(float* __restrict__ p, const float (&v)[
 // ------------------------------------------------------------------------------------------
 // build one tile: NB (neighbour ids), Q (p_j, dist), P (p_i), F (features)
 // ------------------------------------------------------------------------------------------
+// Neighbour ids of a tile, one register per edge this thread builds: fetched one tile ahead (the loads travel during
+// the previous tile's contraction), so that the build starts with the dependent gathers instead of with a load.
+template <class Cfg>
+struct LfaIds {
+  static constexpr int EPT = (Cfg::EDGES + Cfg::THREADS - 1) / Cfg::THREADS;
+  // (K = 32 tables: the backward kernels are at their register limit -- the ids are loaded inside the build there)
+  static constexpr bool AHEAD = (Cfg::KT <= 16);
+  int j[AHEAD ? EPT : 1];
+};
+template <class Cfg>
+__device__ __forceinline__ void lfa_prefetch_ids(LfaIds<Cfg>& ids, int64_t tile_base, int64_t n, int64_t ntiles_end,
+                                                 const int32_t* __restrict__ nbr) {
+  constexpr int KT = Cfg::KT, THREADS = Cfg::THREADS, EDGES = Cfg::EDGES;
+  if constexpr (LfaIds<Cfg>::AHEAD) {
+#pragma unroll
+    for (int it = 0; it < LfaIds<Cfg>::EPT; ++it) {
+      const int e = threadIdx.x + it * THREADS;
+      const int64_t i = tile_base + e / KT;
+      ids.j[it] = (e < EDGES && tile_base < ntiles_end && i < n) ? __ldg(nbr + i * KT + (e % KT)) : -1;
+    }
+  }
+}
+
 template <class Cfg>
 __device__ __forceinline__ void lfa_build_tile(int64_t tile_base, int64_t n, const float* __restrict__ x,
-                                               const float* __restrict__ pos, const int32_t* __restrict__ nbr,
-                                               const float* __restrict__ enc_w, const float* __restrict__ enc_b,
+                                               const float* __restrict__ pos, const LfaIds<Cfg>& ids,
+                                               const int32_t* __restrict__ nbr, const float* __restrict__ enc_w, const float* __restrict__ enc_b,
                                                float* __restrict__ F, float4* __restrict__ Q,
                                                float4* __restrict__ P, int* __restrict__ NB) {
   constexpr int C = Cfg::C, KT = Cfg::KT, H = Cfg::H, THREADS = Cfg::THREADS, EDGES = Cfg::EDGES;
   constexpr int CSTRIDE = Cfg::CSTRIDE;
+  constexpr int H4 = H / 4;
+  constexpr bool GATHER_X_HERE = (H4 <= 2);  // narrow features: the edge's thread also gathers x_j (one latency, not two)
   const int tid = threadIdx.x;
+  const float4* x4 = reinterpret_cast<const float4*>(x);
 
-  for (int e = tid; e < EDGES; e += THREADS) {
+#pragma unroll
+  for (int it = 0; it < LfaIds<Cfg>::EPT; ++it) {
+    const int e = tid + it * THREADS;
+    if (e >= EDGES) break;
     const int g = e / KT, kk = e % KT;
     const int64_t i = tile_base + g;
-    int j = -1;
+    int j;  // -1 beyond n / padded slots
+    if constexpr (LfaIds<Cfg>::AHEAD) {
+      j = ids.j[it];
+    } else {
+      j = (i < n) ? __ldg(nbr + i * KT + kk) : -1;
+    }
     float4 qv = make_float4(0.f, 0.f, 0.f, 0.f);
     float4 pv = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 xv[GATHER_X_HERE ? H4 : 1];
+#pragma unroll
+    for (int m4 = 0; m4 < (GATHER_X_HERE ? H4 : 1); ++m4) xv[m4] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (i < n) {
-      j = __ldg(nbr + i * KT + kk);
       pv = make_float4(__ldg(pos + 3 * i), __ldg(pos + 3 * i + 1), __ldg(pos + 3 * i + 2), 0.f);
       if (j >= 0) {
         const float pjx = __ldg(pos + 3 * (int64_t)j), pjy = __ldg(pos + 3 * (int64_t)j + 1),
                     pjz = __ldg(pos + 3 * (int64_t)j + 2);
+        if constexpr (GATHER_X_HERE) {
+#pragma unroll
+          for (int m4 = 0; m4 < H4; ++m4) xv[m4] = __ldg(x4 + (int64_t)j * H4 + m4);
+        }
         const float dx = pjx - pv.x, dy = pjy - pv.y, dz = pjz - pv.z;
         const float dist = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
         qv = make_float4(pjx, pjy, pjz, dist);
@@ -199,18 +239,22 @@ __device__ __forceinline__ void lfa_build_tile(int64_t tile_base, int64_t n, con
     NB[e] = j;
     Q[e] = qv;
     if (kk == 0) P[g] = pv;
+    if constexpr (GATHER_X_HERE) {
+#pragma unroll
+      for (int m4 = 0; m4 < H4; ++m4) *reinterpret_cast<float4*>(F + g * CSTRIDE + kk * C + m4 * 4) = xv[m4];
+    }
   }
   __syncthreads();
 
   // x_j gather into F[:, 0:H)
-  constexpr int H4 = H / 4;
-  const float4* x4 = reinterpret_cast<const float4*>(x);
-  for (int t = tid; t < EDGES * H4; t += THREADS) {
-    const int e = t / H4, m4 = t % H4;
-    const int j = NB[e];
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (j >= 0) v = __ldg(x4 + (int64_t)j * H4 + m4);
-    *reinterpret_cast<float4*>(F + (e / KT) * CSTRIDE + (e % KT) * C + m4 * 4) = v;
+  if constexpr (!GATHER_X_HERE) {
+    for (int t = tid; t < EDGES * H4; t += THREADS) {
+      const int e = t / H4, m4 = t % H4;
+      const int j = NB[e];
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (j >= 0) v = __ldg(x4 + (int64_t)j * H4 + m4);
+      *reinterpret_cast<float4*>(F + (e / KT) * CSTRIDE + (e % KT) * C + m4 * 4) = v;
+    }
   }
 
   // encoder into F[:, H:C)
@@ -313,9 +357,12 @@ lfa_fwd_kernel(const float* __restrict__ x, const float* __restrict__ pos, const
   const int tid = threadIdx.x;
   const int g = tid / TPC, col0 = (tid % TPC) * CW;
 
+  LfaIds<Cfg> ids;
+  lfa_prefetch_ids<Cfg>(ids, (int64_t)blockIdx.x * TC, n, ntiles * TC, nbr);
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int64_t tile_base = tile * TC;
-    lfa_build_tile<Cfg>(tile_base, n, x, pos, nbr, enc_w, enc_b, F, Q, P, NB);
+    lfa_build_tile<Cfg>(tile_base, n, x, pos, ids, nbr, enc_w, enc_b, F, Q, P, NB);
+    lfa_prefetch_ids<Cfg>(ids, (tile + gridDim.x) * TC, n, ntiles * TC, nbr);  // next tile: in flight during the contraction
 
     float acc[KT][CW];
 #pragma unroll
@@ -441,9 +488,12 @@ lfa_bwd_kernel(const float* __restrict__ x, const float* __restrict__ pos, const
 #pragma unroll
     for (int t = 0; t < 8; ++t) ge_reg[cw][t] = 0.f;
 
+  LfaIds<Cfg> ids;
+  lfa_prefetch_ids<Cfg>(ids, (int64_t)blockIdx.x * TC, n, ntiles * TC, nbr);
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int64_t tile_base = tile * TC;
-    lfa_build_tile<Cfg>(tile_base, n, x, pos, nbr, enc_w, enc_b, F, Q, P, NB);
+    lfa_build_tile<Cfg>(tile_base, n, x, pos, ids, nbr, enc_w, enc_b, F, Q, P, NB);
+    lfa_prefetch_ids<Cfg>(ids, (tile + gridDim.x) * TC, n, ntiles * TC, nbr);  // next tile: in flight during the contraction
 
     float acc[KT][CW];
 #pragma unroll
