@@ -807,7 +807,7 @@ extern "C" int b200_edge_moments(const float* pos, const int32_t* nbr, int64_t n
 #define B200_LFA_BWD_CASES(X) \
   X(8, 16, 2, 32, false) X(16, 16, 2, 16, false, 3) X(32, 16, 2, 8, false, 3) \
   X(64, 16, 4, 8, true) X(128, 16, 4, 4, true) X(256, 16, 4, 2, true) \
-  X(8, 32, 2, 32, false) X(16, 32, 4, 32, false) X(32, 32, 4, 16, false) \
+  X(8, 32, 2, 32, false) X(16, 32, 2, 16, false, 3) X(32, 32, 2, 8, false, 3) \
   X(64, 32, 4, 4, true) X(128, 32, 4, 2, true) X(256, 32, 4, 2, true)
 
 extern "C" int b200_lfa_fwd(const float* x, const float* pos, const int32_t* nbr, const float* enc_w,

@@ -691,7 +691,11 @@ static int launch_lfa_tc(const float* x, const float* pos, const int32_t* nbr, c
 // (C, KT, NE forward, NE backward).  Tile sizes: every epilogue thread gets >= 1 centre (NE / KT a multiple of
 // 2 * 128 / C), shared memory <= 227 KB, W columns + 2 * (NE + C) TMEM columns <= 512.
 // K = 32 neighbour tables (BASELINE configs[4]) would need twice the shared memory per centre: FMA kernels.
-#define B200_LFA_TC_CASES(X) X(32, 16, 128, 128) X(64, 16, 128, 128) X(128, 16, 128, 32)
+// (C, KT, edges per forward tile, edges per backward tile).  K = 32 tables (BASELINE configs[4]): c = 64 both ways;
+// c = 128 forward only -- its backward tile (W_att in shared memory + dA, F, T planes for >= 2 centres of 32 edges) does
+// not fit 227 KB, the FMA kernel stays; c = 32 would need 8 centres x 32 edges = 256 TMEM columns per slot.
+#define B200_LFA_TC_CASES(X) X(32, 16, 128, 128) X(64, 16, 128, 128) X(128, 16, 128, 32) X(64, 32, 128, 128)
+#define B200_LFA_TC_FWD_ONLY_CASES(X) X(128, 32, 64, 0)
 
 // returns B200_E_UNSUPPORTED when this (c, kt) has no tensor-core kernel (the caller then uses the FMA kernel)
 int lfa_tc_fwd_dispatch(const float* x, const float* pos, const int32_t* nbr, const float* enc_w, const float* enc_b,
@@ -702,6 +706,7 @@ int lfa_tc_fwd_dispatch(const float* x, const float* pos, const int32_t* nbr, co
     return launch_lfa_tc<C_, NEF_, KT_, false>(x, pos, nbr, enc_w, enc_b, nullptr, att_wt, out, nullptr, nullptr, nullptr, \
                                                nullptr, nullptr, nullptr, n, st);
   B200_LFA_TC_CASES(X)
+  B200_LFA_TC_FWD_ONLY_CASES(X)
 #undef X
   return B200_E_UNSUPPORTED;
 }

@@ -219,7 +219,8 @@ def test_lfa_module_parity(lib, c, k, training):
             assert_close(b, dict(ref.named_buffers())[name], atol=1e-5, rtol=1e-5, what=name)
 
 
-@pytest.mark.parametrize("c,k,big", [(32, 16, False), (64, 16, False), (128, 16, False), (64, 16, True), (128, 16, True)])
+@pytest.mark.parametrize("c,k,big", [(32, 16, False), (64, 16, False), (128, 16, False), (64, 16, True), (128, 16, True),
+                                     (64, 32, False), (64, 32, True), (128, 32, False), (64, 20, False)])
 def test_lfa_tensor_core_path_vs_fma_and_fp64(lib, c, k, big):
     """The tcgen05 (3xTF32, TMEM) fused LFA forward AND backward (lfa_tc.cu, the production path for c in
     {32, 64, 128}) against (a) the fp32 FMA kernels of lfa.cu (`b200_set_option("tensor_cores", 0)`) and (b) an fp64
