@@ -48,6 +48,8 @@ int b200_check_device(void);
  *   "tensor_core_paths"  bitmask (default 31) of the kernel families allowed on the tensor cores while "tensor_cores" is 1:
  *                   1 Linear forward, 2 Linear input gradient, 4 wide weight gradient, 8 narrow weight gradient,
  *                   16 fused LFA forward/backward.  Used to attribute numerical differences to one family.
+ *   "knn_points_per_cell"  average occupancy of the bucket grid of b200_knn_grid; 0 (default) = automatic
+ *                   (6 for k < 8, 8 for k < 24, 16 above); results do not depend on it (exact search).
  *   "tc_timeline"   device pointer (as integer) to 128 int64 receiving clock64() marks of CTA 0 of the tcgen05 GEMMs
  *                   (scripts/tc_timeline.py); 0 (default) = off.
  * b200_get_option returns the current value, -1 for an unknown key. */

@@ -70,6 +70,8 @@ int linear_rows_grid(int64_t n);
 int launch_linear_rows(const float* a1, int64_t ld1, int c1, const float* a2, int64_t ld2, int c2, const float* w, int w_ld,
                        bool w_out_major, const float* bias, float* o1, int64_t old1, int oc1, float* o2, int64_t old2, int oc2,
                        int64_t n, double* colstats, cudaStream_t st);
+void set_grid_points_per_cell(int v);  // knn_grid.cu (tuning knob, b200_set_option("knn_points_per_cell"))
+int get_grid_points_per_cell();
 bool tc_path_enabled(int bit);  // runtime.cu: b200_set_option("tensor_core_paths", mask) -- per-kernel-family A/B switch
 bool tensor_cores_enabled();  // runtime.cu: b200_set_option("tensor_cores", 0) selects the FMA kernels (A/B switch)
 

@@ -23,6 +23,8 @@
 // hence not on the (atomic, non-deterministic) order of points inside a cell.
 #include <math_constants.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace b200 {
@@ -41,8 +43,20 @@ struct GridMeta {
   int pad0, pad1;
 };
 
-__host__ __device__ __forceinline__ int grid_cells_for(long long n) {
-  int g = (int)sqrtf((float)n / GRID_POINTS_PER_CELL);
+// average points per (2-D) cell; b200_set_option("knn_points_per_cell", v) overrides the default for tuning runs
+static std::atomic<int> g_grid_ppc{0};  // 0 = automatic (by k, below)
+void set_grid_points_per_cell(int v) { g_grid_ppc.store(v < 0 ? 0 : (v > 64 ? 64 : v), std::memory_order_relaxed); }
+int get_grid_points_per_cell() { return g_grid_ppc.load(std::memory_order_relaxed); }
+// Measured (scripts/knn_ppc_sweep.py, 16 x 12 800 points k = 16 / 4 x 65 536 points k = 32): 6 points per cell 496 / 1605 us,
+// 8: 468 / 1523, 16: 458 / 1407 -- fewer, fuller cells mean fewer half-empty candidate batches per ring row.
+static float grid_ppc_for(int k) {
+  const int v = get_grid_points_per_cell();
+  if (v > 0) return (float)v;
+  return k >= 24 ? 16.f : (k >= 8 ? 8.f : GRID_POINTS_PER_CELL);
+}
+
+__host__ __device__ __forceinline__ int grid_cells_for(long long n, float ppc) {
+  int g = (int)sqrtf((float)n / ppc);
   if (g < 1) g = 1;
   if (g > GRID_MAX_G) g = GRID_MAX_G;
   return g;
@@ -57,7 +71,7 @@ __device__ __forceinline__ int grid_cell_1d(float p, float o, float inv, int g) 
 // ---- 1. per-cloud bounding box and grid geometry
 __global__ void __launch_bounds__(256)
 grid_meta_kernel(const float* __restrict__ pos, const int64_t* __restrict__ ptr, GridMeta* __restrict__ meta,
-                 int* __restrict__ counts, int stride) {
+                 int* __restrict__ counts, int stride, float ppc) {
   const int cloud = blockIdx.x;
   const int64_t xs = ptr[cloud], xe = ptr[cloud + 1];
   float lo[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F};
@@ -82,7 +96,7 @@ grid_meta_kernel(const float* __restrict__ pos, const int64_t* __restrict__ ptr,
     if (lane == 0) slo[warp][d] = lo[d], shi[warp][d] = hi[d];
   }
   __syncthreads();
-  const int g = grid_cells_for(xe - xs);
+  const int g = grid_cells_for(xe - xs, ppc);
   if (threadIdx.x == 0) {
     float ext[3];
 #pragma unroll
@@ -134,9 +148,9 @@ grid_count_kernel(const float* __restrict__ pos, const int64_t* __restrict__ ptr
 
 // ---- 3. exclusive scan of the cell counters (one CTA per cloud); counters become scatter cursors
 __global__ void __launch_bounds__(256)
-grid_scan_kernel(const int64_t* __restrict__ ptr, int* __restrict__ counts, int* __restrict__ starts, int stride) {
+grid_scan_kernel(const int64_t* __restrict__ ptr, int* __restrict__ counts, int* __restrict__ starts, int stride, float ppc) {
   const int cloud = blockIdx.x;
-  const int g = grid_cells_for(ptr[cloud + 1] - ptr[cloud]);
+  const int g = grid_cells_for(ptr[cloud + 1] - ptr[cloud], ppc);
   const int cells = g * g;
   int* cnt = counts + (int64_t)cloud * stride;
   int* st = starts + (int64_t)cloud * (stride + 1);
@@ -371,14 +385,16 @@ knn_grid_warp_kernel(const float4* __restrict__ sorted, const int* __restrict__ 
             if (a1 <= g - 1) s2 = row[a1], e2 = row[a1 + 1];
           }
         }
-#pragma unroll 1
-        for (int pass = 0; pass < 2; ++pass) {
-          const int s = pass ? s2 : s1, e = pass ? e2 : e1;
-          int len = e - s;
+        {
+          // the two runs of an interior row (left and right cell) are walked as ONE concatenated run: half as many
+          // candidate batches there, fuller lanes
+          const int len1 = e1 - s1, mine = len1 + (e2 - s2);
+          int len = mine;
           if (LANES < 32) len = max(len, __shfl_xor_sync(FULL, len, 16));  // the longer of the two groups' runs
           for (int u0 = 0; u0 < len; u0 += LANES) {
-            const int u = s + u0 + lg;
-            const bool valid = u < e;
+            const int uu = u0 + lg;
+            const int u = (uu < len1) ? (s1 + uu) : (s2 + (uu - len1));
+            const bool valid = uu < mine;
             float dc = CUDART_INF_F;
             int ic = 0x7fffffff;
             if (valid) {
@@ -482,7 +498,9 @@ using namespace b200;
 
 extern "C" int64_t b200_knn_grid_workspace_bytes(int64_t nx, int32_t num_clouds, int64_t max_x_per_cloud) {
   if (nx < 0 || num_clouds < 0 || max_x_per_cloud < 0) return -1;
-  const int g = grid_cells_for(max_x_per_cloud);
+  // (sized for the finest grid any k may ask for)
+  const int v = get_grid_points_per_cell();
+  const int g = grid_cells_for(max_x_per_cloud, v > 0 ? (float)v : GRID_POINTS_PER_CELL);
   return (int64_t)carve(nullptr, nx, num_clouds, g * g).bytes;
 }
 
@@ -497,7 +515,8 @@ extern "C" int b200_knn_grid(const float* pos_x, const int64_t* ptr_x, int64_t n
   B200_REQUIRE(num_clouds >= 0 && num_clouds <= 65535, B200_E_UNSUPPORTED, "b200_knn_grid: num_clouds=%d out of [0,65535]", num_clouds);
   B200_REQUIRE(((uintptr_t)workspace & 255) == 0, B200_E_INVALID, "b200_knn_grid: workspace must be 256-byte aligned");
   if (ny == 0 || num_clouds == 0 || max_y_per_cloud <= 0) return B200_OK;
-  const int g = grid_cells_for(max_x_per_cloud);
+  const float ppc = grid_ppc_for(k);
+  const int g = grid_cells_for(max_x_per_cloud, ppc);
   const int stride = g * g;
   const GridWorkspace w = carve(workspace, nx, num_clouds, stride);
   B200_REQUIRE((int64_t)w.bytes <= workspace_bytes, B200_E_INVALID, "b200_knn_grid: workspace too small (%lld < %lld)",
@@ -505,18 +524,18 @@ extern "C" int b200_knn_grid(const float* pos_x, const int64_t* ptr_x, int64_t n
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool self = (pos_x == pos_y) && (ptr_x == ptr_y) && (nx == ny);
 
-  grid_meta_kernel<<<(unsigned)num_clouds, 256, 0, st>>>(pos_x, ptr_x, w.meta, w.counts, stride);
+  grid_meta_kernel<<<(unsigned)num_clouds, 256, 0, st>>>(pos_x, ptr_x, w.meta, w.counts, stride, ppc);
   B200_CHECK_LAUNCH("grid_meta_kernel");
   if (max_x_per_cloud > 0) {
     dim3 pgrid((unsigned)ceil_div(max_x_per_cloud, 256), (unsigned)num_clouds);
     grid_count_kernel<<<pgrid, 256, 0, st>>>(pos_x, ptr_x, w.meta, w.counts, w.cell_of, stride);
     B200_CHECK_LAUNCH("grid_count_kernel");
-    grid_scan_kernel<<<(unsigned)num_clouds, 256, 0, st>>>(ptr_x, w.counts, w.starts, stride);
+    grid_scan_kernel<<<(unsigned)num_clouds, 256, 0, st>>>(ptr_x, w.counts, w.starts, stride, ppc);
     B200_CHECK_LAUNCH("grid_scan_kernel");
     grid_scatter_kernel<<<pgrid, 256, 0, st>>>(pos_x, ptr_x, w.counts, w.cell_of, w.sorted, stride);
     B200_CHECK_LAUNCH("grid_scatter_kernel");
   } else {
-    grid_scan_kernel<<<(unsigned)num_clouds, 256, 0, st>>>(ptr_x, w.counts, w.starts, stride);
+    grid_scan_kernel<<<(unsigned)num_clouds, 256, 0, st>>>(ptr_x, w.counts, w.starts, stride, ppc);
     B200_CHECK_LAUNCH("grid_scan_kernel");
   }
   if ((kt == 16 || kt == 32) && k > 1) {  // kNN graph / k = 10 interpolation: warp-cooperative search

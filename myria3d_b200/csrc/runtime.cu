@@ -63,6 +63,10 @@ int b200_set_option(const char* key, int64_t value) {
     b200::g_tensor_cores.store(value != 0, std::memory_order_relaxed);
     return B200_OK;
   }
+  if (strcmp(key, "knn_points_per_cell") == 0) {
+    b200::set_grid_points_per_cell((int)value);
+    return B200_OK;
+  }
   if (strcmp(key, "tensor_core_paths") == 0) {
     b200::g_tc_paths.store((int)value, std::memory_order_relaxed);
     return B200_OK;
@@ -71,12 +75,13 @@ int b200_set_option(const char* key, int64_t value) {
     b200::g_tc_timeline.store(reinterpret_cast<long long*>(static_cast<intptr_t>(value)), std::memory_order_relaxed);
     return B200_OK;
   }
-  b200::set_error("b200_set_option: unknown option '%s' (known: tensor_cores, tensor_core_paths, tc_timeline)", key);
+  b200::set_error("b200_set_option: unknown option '%s' (known: tensor_cores, tensor_core_paths, knn_points_per_cell, tc_timeline)", key);
   return B200_E_INVALID;
 }
 
 int64_t b200_get_option(const char* key) {
   if (key && strcmp(key, "tensor_cores") == 0) return b200::g_tensor_cores.load(std::memory_order_relaxed);
+  if (key && strcmp(key, "knn_points_per_cell") == 0) return b200::get_grid_points_per_cell();
   if (key && strcmp(key, "tensor_core_paths") == 0) return b200::g_tc_paths.load(std::memory_order_relaxed);
   if (key && strcmp(key, "tc_timeline") == 0)
     return static_cast<int64_t>(reinterpret_cast<intptr_t>(b200::g_tc_timeline.load(std::memory_order_relaxed)));
