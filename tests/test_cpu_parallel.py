@@ -1,4 +1,5 @@
-"""world_size-2 gloo tests (CPU) of the data-parallel plumbing: flat gradient all-reduce, tile sharding."""
+"""world_size-2 gloo tests (CPU) of the data-parallel plumbing: flat gradient all-reduce, BatchNorm-buffer broadcast
+(torch DDP's broadcast_buffers=True), tile sharding."""
 import os
 
 import torch
@@ -32,6 +33,21 @@ def _worker(rank, world, port, q):
     red.zero_grad()
     ok = ok and float(net[2].bias.grad.abs().sum()) == 0.0
     ok = ok and shard_tiles(5, rank, world) == ([0, 2, 4] if rank == 0 else [1, 3, 0])
+    # DDP's broadcast_buffers=True: after the (rank-dependent) forward above the BatchNorm running statistics differ;
+    # broadcast_buffers() / its start + finish halves make every rank hold rank 0's, integer counters untouched
+    rm_mine = net[1].running_mean.clone()
+    rms = [torch.zeros_like(rm_mine) for _ in range(world)]
+    dist.all_gather(rms, rm_mine)
+    ok = ok and not torch.equal(rms[0], rms[1])
+    nbt = int(net[1].num_batches_tracked)
+    work = red.start_broadcast()
+    red.finish_broadcast(work)
+    ok = ok and torch.equal(net[1].running_mean, rms[0]) and int(net[1].num_batches_tracked) == nbt
+    net[1].running_var.add_(float(rank))
+    red.broadcast_buffers()
+    rvs = [torch.zeros_like(rm_mine) for _ in range(world)]
+    dist.all_gather(rvs, net[1].running_var.clone())
+    ok = ok and torch.equal(rvs[0], rvs[1])
     q.put((rank, bool(ok)))
     dist.barrier()
     dist.destroy_process_group()
