@@ -253,3 +253,45 @@ def test_autograd_path_is_used_without_a_flat_reducer(lib):
     for n, p in ref.named_parameters():
         scale = float(p.grad.abs().max()) + 1e-12
         assert float((g_ddp[n] - p.grad).abs().max()) <= 1e-4 * scale + 1e-6, n  # (+ fp32 noise of zero gradients)
+
+
+def test_prefetch_feeds_the_next_replay(lib):
+    """GraphedTrainStep.prefetch: the next (pinned) host batch is copied on a side stream while a step runs; the step
+    called with that batch object then trains on exactly its data (static inputs == the batch), an unrelated batch object
+    of the same layout falls back to the direct copy, and the loss of a prefetched step equals the eager loss."""
+    from myria3d_b200.graphed import GraphedTrainStep
+    from myria3d_b200.parallel import FlatGradAllReducer
+
+    m = _model(5)
+    m.model.mlp_classif.dropout = [0.0, 0.0]
+    opt = torch.optim.Adam(m.parameters(), lr=1e-3, capturable=True)
+    step = GraphedTrainStep(m, opt, FlatGradAllReducer(m))
+    b1, b2, b3 = (_batch([700, 500], s).pin_memory() for s in (11, 12, 13))
+    assert step.prefetch(b1) is False  # nothing captured yet: a no-op
+    step(b1)
+    key = tuple(b1.ptr.tolist())
+    cap = step._captured[key]
+    assert step.prefetch(b2) is True
+    snap = copy.deepcopy(m)
+    loss2 = float(step(b2))  # consumes the staged copy
+    torch.cuda.synchronize()
+    for k in ("x", "pos", "y", "batch"):
+        assert torch.equal(cap.static[k].cpu(), getattr(b2, k)), k
+    snap.model.injected_decimation_idx = [t.clone() for t in cap.idx_static]
+    out = snap.training_step(b2.to(DEV), 0)
+    assert abs(float(out["loss"].detach()) - loss2) < 1e-4
+    # prefetch b3, but call with b1: the staged copy must not be used
+    step.prefetch(b3)
+    step(b1)
+    torch.cuda.synchronize()
+    assert torch.equal(cap.static["pos"].cpu(), b1.pos)
+    step(b3)  # now the staged copy of b3 is consumed
+    torch.cuda.synchronize()
+    assert torch.equal(cap.static["x"].cpu(), b3.x)
+    # a running loop: prefetch behind every replay
+    step.prefetch(b1)
+    for cur, nxt in ((b1, b2), (b2, b3), (b3, b1)):
+        loss = step(cur)
+        step.prefetch(nxt)
+        assert torch.isfinite(loss).item()
+        assert torch.equal(cap.static["y"].cpu(), cur.y)
