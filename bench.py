@@ -320,35 +320,45 @@ def run_reference(args):
         "impl": "reference", "metric": metric_name(args), "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, 1, "reference"),
+        "config": workload_config(args, max(int(args.gpus), 1), "reference"), "impl_detail": impl_detail(args, "reference"),
         "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    if args.config == "D":
-        line["config"]["step"] = ("inference only, reference CPU path: eval forward + k=10 interpolation + stitch on a bounded "
-                                  f"sample of {args.cpu_tiles} window(s) per step; value counts FULL-cloud points")
-        line["config"]["points_per_step"] = args.cpu_tiles * FULL_POINTS
     print(json.dumps(line), flush=True)
 
 
 def workload_config(args, world, impl="b200"):
+    """`config`: the WORKLOAD, identical in the b200 and the reference arm (the driver compares the two lines)."""
     which = {"B": "configs[1]" + ("/[2]" if world > 1 else ""), "E": "configs[4]", "D": "configs[3]"}[args.config]
+    per_tile = FULL_POINTS if args.config == "D" else args.points
     return {
         "workload": f"RandLA-Net full (4 down/4 up), K={K_NEIGHBORS}, {args.points} pts/tile, batch={args.tiles}/GPU "
                     f"(BASELINE {which})",
+        "num_features": NUM_FEATURES, "num_classes": NUM_CLASSES, "global_batch_tiles": args.tiles * world,
+        "points_per_step": args.tiles * per_tile * world, "parallelism": f"dp{world}",
+        "l2": "GPU arm: 256 MiB buffer rewritten between timed steps (outside the event pairs), rotating input batches; "
+              "CPU arm: not applicable",
+    }
+
+
+def impl_detail(args, impl="b200"):
+    """How this arm runs the workload (kept out of `config` so that both arms print the same `config`)."""
+    if args.config == "D":
+        step = ("inference only: eval forward + k=10 interpolation of the logits to the 60 000-point windows + sliding-window "
+                "stitch (scatter-sum, softmax, argmax, entropy); value counts FULL-cloud points")
+        if impl == "reference":
+            step += f"; reference CPU path on a bounded sample of {args.cpu_tiles} window(s) per step"
+        return {"step": step}
+    return {
         "optimizer": ("torch.optim.Adam (CPU)" if impl == "reference" else
                       "torch.optim.Adam(fused)" if getattr(args, "torch_adam", False) else "FlatAdam (b200_adam_flat)"),
         "step": "fwd + CrossEntropyLoss + bwd + flat NCCL grad all-reduce (N>1) + Adam; "
                 + ("reference CPU path: eager PyTorch, bounded sample of "
                    f"{args.cpu_tiles} tiles per step" if impl == "reference" else
                    ("eager launches" if args.eager else "whole step replayed as one CUDA graph (GraphedTrainStep)")),
-        "num_features": NUM_FEATURES, "num_classes": NUM_CLASSES, "global_batch_tiles": args.tiles * world,
-        "points_per_step": args.tiles * args.points * world,
-        "decimation_rng": args.decimation_rng, "parallelism": f"dp{world}", "l2": "256 MiB buffer rewritten between timed steps (outside the event pairs); "
-                                           "4 rotating input batches",
+        "decimation_rng": "per-cloud torch.randperm" if impl == "reference" else args.decimation_rng,
     }
-
 
 
 # ------------------------------------------------------------------------------ config D: predict path
@@ -526,12 +536,10 @@ def run_b200_predict(args):
             res = cpu_reference_predict(args.cpu_tiles, args.points, args.cpu_steps, 1)
             cpu = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
         cfg = workload_config(args, world)
-        cfg["step"] = ("inference only: eval forward + k=10 interpolation of the logits to the 60 000-point windows + "
-                       "sliding-window stitch (scatter-sum, softmax, argmax, entropy); value counts FULL-cloud points")
-        cfg["points_per_step"] = pts * world
         line = {"metric": "points/sec (predict path) RandLA-Net 40960-pt tiles", "value": pts * world / (ms * 1e-3), "unit": UNIT,
                 "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg, "clocks": clocks,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+                "impl_detail": impl_detail(args), "clocks": clocks,
                 "gpu_launches": int(launches),
                 "e2e": {"value": pts * world / (e2e_ms / args.steps * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                         "d2h_bytes_per_step": int(out_host.numel() * 8), "ms_per_step": e2e_ms / args.steps},
@@ -734,6 +742,7 @@ def run_b200(args):
             "metric": metric_name(args), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
+            "impl_detail": impl_detail(args),
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": 4,
                     "ms_per_step": e2e_ms / args.steps,
