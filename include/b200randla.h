@@ -48,6 +48,9 @@ int b200_check_device(void);
  *   "tensor_core_paths"  bitmask (default 31) of the kernel families allowed on the tensor cores while "tensor_cores" is 1:
  *                   1 Linear forward, 2 Linear input gradient, 4 wide weight gradient, 8 narrow weight gradient,
  *                   16 fused LFA forward/backward.  Used to attribute numerical differences to one family.
+ *   "tma_rows"      bitmask of the Linear kernels of the 16/32/64-channel layers on >= 8192 rows that run as TMA-fed
+ *                   persistent row-streaming kernels (tma_rows.cu; 2-D tensor maps, mbarrier ring): 1 forward,
+ *                   2 input gradient, 4 weight gradient (default 7); cleared bits select the register-staged kernels.
  *   "knn_points_per_cell"  average occupancy of the bucket grid of b200_knn_grid; 0 (default) = automatic
  *                   (6 for k < 8, 8 for k < 24, 16 above); results do not depend on it (exact search).
  *   "tc_timeline"   device pointer (as integer) to 128 int64 receiving clock64() marks of CTA 0 of the tcgen05 GEMMs

@@ -114,6 +114,12 @@ def load() -> ctypes.CDLL:
         fn.argtypes = argtypes
     if lib.b200_abi_version() != ABI_VERSION:
         raise B200Error(f"ABI mismatch: library {lib.b200_abi_version()} != binding {ABI_VERSION}")
+    # A/B switches for scripts (bench.py, scripts/microbench.py): B200_OPTIONS="tma_rows=0,knn_points_per_cell=8" is applied
+    # HERE, by the Python binding, through the public b200_set_option -- the library itself reads no environment.
+    for item in filter(None, os.environ.get("B200_OPTIONS", "").split(",")):
+        key, _, value = item.partition("=")
+        if lib.b200_set_option(key.strip().encode(), int(value)) != 0:
+            raise B200Error(f"B200_OPTIONS: {lib.b200_last_error().decode('utf-8', 'replace')}")
     _lib = lib
     return lib
 

@@ -70,6 +70,19 @@ int linear_rows_grid(int64_t n);
 int launch_linear_rows(const float* a1, int64_t ld1, int c1, const float* a2, int64_t ld2, int c2, const float* w, int w_ld,
                        bool w_out_major, const float* bias, float* o1, int64_t old1, int oc1, float* o2, int64_t old2, int oc2,
                        int64_t n, double* colstats, cudaStream_t st);
+// tma_rows.cu: TMA-fed row-streaming kernels for the 16/32/64-channel layers on >= 8192 rows.  NN serves the forward
+// (w_out_major: w is [mcols][K]) and the input gradient (w is [K][mcols]); num_partials = rows of the caller's colstats
+// buffer (one per CTA is written, the rest zero-filled).  TN is the weight / bias gradient (gw, gb accumulate).
+bool tma_rows_enabled(int bit);  // runtime.cu: b200_set_option("tma_rows", mask): 1 forward, 2 input gradient, 4 weight gradient
+bool tma_rows_nn_ok(int64_t n, const float* a1, int64_t ld1, int c1, const float* a2, int64_t ld2, int c2, int mcols,
+                    const float* o1, int64_t old1, int oc1, const float* o2, int64_t old2);
+int launch_tma_rows_nn(const float* a1, int64_t ld1, int c1, const float* a2, int64_t ld2, int c2, const float* w, int w_ld,
+                       bool w_out_major, const float* bias, float* o1, int64_t old1, int oc1, float* o2, int64_t old2,
+                       int mcols, int64_t n, double* colstats, int num_partials, cudaStream_t st);
+bool tma_rows_tn_ok(int64_t n, const float* gy, int cout, const float* a1, int64_t ld1, int c1, const float* a2, int64_t ld2,
+                    int c2);
+int launch_tma_rows_tn(const float* gy, int cout, const float* a1, int64_t ld1, int c1, const float* a2, int64_t ld2, int c2,
+                       float* gw, float* gb, int64_t n, cudaStream_t st);
 void set_grid_points_per_cell(int v);  // knn_grid.cu (tuning knob, b200_set_option("knn_points_per_cell"))
 int get_grid_points_per_cell();
 bool tc_path_enabled(int bit);  // runtime.cu: b200_set_option("tensor_core_paths", mask) -- per-kernel-family A/B switch

@@ -896,6 +896,10 @@ extern "C" int b200_linear_fwd(const float* a1, int64_t ld1, int32_t c1, const f
   B200_REQUIRE(ld1 >= c1 && (c2 == 0 || ld2 >= c2), B200_E_INVALID, "b200_linear_fwd: row stride < width");
   if (n <= 0) return B200_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // 16/32/64-channel layers of levels 0-1: TMA-fed persistent row streaming (tma_rows.cu)
+  if (tma_rows_enabled(1) && tma_rows_nn_ok(n, a1, ld1, c1, a2, ld2, c2, cout, y, cout, cout, nullptr, 0))
+    return launch_tma_rows_nn(a1, ld1, c1, a2, ld2, c2, w, c1 + c2, true, bias, y, cout, cout, nullptr, 0, cout, n, colstats,
+                              colstats ? (int)b200_linear_fwd_num_stat_partials(n, c1, c2, cout) : 0, st);
   if (tc_nt_shape_ok(n, c1, c2, cout) && tc_path_enabled(1))  // tcgen05 (3xTF32): every layer with >= 64 input and output channels
     return launch_tc_nt(a1, ld1, c1, a2, ld2, c2, w, cout, bias, y, cout, cout, nullptr, 0, colstats, n, st);
   if (linear_rows_ok(n, c1 + c2, cout))  // narrow layers of levels 0-1: one thread per row (linear_rows.cu)
@@ -934,6 +938,10 @@ extern "C" int b200_linear_bwd_input(const float* grad_y, const float* w, float*
   if (n <= 0 || (!ga1 && !ga2)) return B200_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int ktot = c1 + c2;
+  if (tma_rows_enabled(2) &&
+      tma_rows_nn_ok(n, grad_y, cout, cout, nullptr, 0, 0, ktot, ga1, ldg1, c1, ga2, ldg2))
+    return launch_tma_rows_nn(grad_y, cout, cout, nullptr, 0, 0, w, ktot, false, nullptr, ga1, ldg1, c1, ga2, ldg2, ktot, n,
+                              nullptr, 0, st);
   if (workspace && workspace_bytes >= (int64_t)ktot * cout * (int64_t)sizeof(float) && aligned16(workspace) &&
       bwd_input_uses_tc(n, ktot, cout)) {
     // tcgen05: grad_a[i][k] = sum_m grad_y[i][m] * W^T[k][m]; W^T goes to the workspace first (<= 1.5 MB)
@@ -976,6 +984,8 @@ extern "C" int b200_linear_bwd_weight(const float* grad_y, const float* a1, int6
   const CatRows A = make_cat(a1, ld1, c1, a2, ld2, c2);
   B200_REQUIRE(!workspace || (reinterpret_cast<uintptr_t>(workspace) & 15) == 0, B200_E_INVALID,
                "b200_linear_bwd_weight: workspace must be 16-byte aligned");
+  if (tma_rows_enabled(4) && tma_rows_tn_ok(n, grad_y, cout, a1, ld1, c1, a2, ld2, c2))
+    return launch_tma_rows_tn(grad_y, cout, a1, ld1, c1, a2, ld2, c2, grad_w, grad_bias, n, st);
   return launch_tn(grad_y, cout, A, grad_w, grad_bias, n, static_cast<float*>(workspace),
                    workspace ? (size_t)workspace_bytes : 0, st);
 }

@@ -259,8 +259,17 @@ tc_reduce_partials_kernel(const float* __restrict__ partial, int splits, int cou
   const int64_t total = (int64_t)cout * ncols, slab = (int64_t)cout * ncols_pad;
   for (int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x; t < total; t += (int64_t)gridDim.x * 256) {
     const int m = (int)(t / ncols), c = (int)(t % ncols);
+    // up to 148 splits: eight independent loads in flight per thread instead of one dependent chain of L2 round trips
+    const float* src = partial + (int64_t)m * ncols_pad + c;
     float acc = 0.f;
-    for (int s = 0; s < splits; ++s) acc += __ldg(partial + (int64_t)s * slab + (int64_t)m * ncols_pad + c);
+    int s = 0;
+    for (; s + 8 <= splits; s += 8) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __ldg(src + (int64_t)(s + u) * slab);
+      acc += ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+    }
+    for (; s < splits; ++s) acc += __ldg(src + (int64_t)s * slab);
     if (c < ktot)
       gw[(int64_t)m * ktot + c] += acc;
     else

@@ -100,7 +100,8 @@ for l, c in [(0, 8), (0, 16), (1, 32), (1, 64), (2, 64), (2, 128), (3, 128), (3,
     bench("lfa_bwd", f"{c}@L{l}", bwd, alg_bytes=nt * (8 * c + 12 + 4 * K), flops=E * (6 * c * c + 4 * 7 * h))
 
 # per-point layers: (level, c1, c2, cout)
-for l, c1, c2, cout in [(0, 9, 0, 32), (0, 32, 0, 32), (0, 32, 0, 4), (0, 16, 0, 32), (0, 32, 32, 32), (0, 32, 0, 64), (0, 64, 0, 32),
+for l, c1, c2, cout in [(0, 9, 0, 32), (0, 32, 0, 32), (0, 32, 0, 4), (0, 16, 0, 32), (0, 32, 32, 32), (0, 32, 0, 64), (0, 64, 0, 32), (0, 16, 0, 16),
+                        (1, 32, 0, 16), (1, 32, 0, 32), (1, 64, 0, 64),
                         (1, 32, 0, 128), (1, 64, 0, 128), (1, 128, 32, 32), (2, 128, 0, 256), (2, 256, 128, 128),
                         (3, 256, 0, 512), (3, 512, 256, 256), (4, 512, 0, 512)]:
     nt = LEVELS[l][0]

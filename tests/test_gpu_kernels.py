@@ -369,6 +369,90 @@ def test_linear_row_streaming_kernel(lib, n, c1, c2, cout):
         assert rel_err(a2g.grad, ga_ref[:, c1:]) < 2e-6
 
 
+@pytest.mark.parametrize("n,c1,c2,cout", [(204800, 32, 0, 32), (51200, 16, 0, 32), (8269, 32, 32, 32), (30000, 64, 0, 32),
+                                          (20000, 32, 0, 64), (9000, 16, 0, 16), (12345, 64, 0, 64), (10000, 32, 0, 16),
+                                          (8200, 16, 0, 64), (40001, 64, 0, 16), (204800, 32, 32, 32)])
+def test_linear_tma_rows(lib, n, c1, c2, cout):
+    """tma_rows.cu (2-D tensor-map TMA boxes through an mbarrier ring, persistent CTAs; 16/32/64-channel layers on
+    >= 8192 rows): forward + fp64 BatchNorm column statistics (|mean| >> std), input gradients of both segments, weight
+    and bias gradients vs fp64, ragged last tile (rows past n are zero-filled by the TMA unit), and agreement with the
+    register-staged kernels the option bits replace."""
+    from myria3d_b200 import ops
+
+    g = torch.Generator().manual_seed(n + cout)
+    a1 = torch.randn(n, c1, generator=g) + 0.2
+    a2 = torch.randn(n, c2, generator=g) if c2 else None
+    w = torch.randn(cout, c1 + c2, generator=g) / (c1 + c2) ** 0.5
+    b = torch.randn(cout, generator=g) + 30.0  # |mean| >> std
+    gy = torch.randn(n, cout, generator=g)
+    inp = (torch.cat([a1, a2], 1) if c2 else a1).double()
+    y_ref = inp @ w.double().t() + b.double()
+    ga_ref = gy.double() @ w.double()
+    gw_ref = gy.double().t() @ inp
+    gb_ref = gy.double().sum(0)
+
+    def run():
+        ag = [t.to(DEV).requires_grad_(True) for t in (a1, w, b)] + ([a2.to(DEV).requires_grad_(True)] if c2 else [])
+        y, stats = ops.linear(ag[0], ag[1], ag[2], a2=ag[3] if c2 else None, want_stats=True)
+        y.backward(gy.to(DEV))
+        torch.cuda.synchronize()
+        return y.detach(), stats, ag
+
+    before = int(lib.b200_get_option(b"tma_rows"))
+    try:
+        lib.b200_set_option(b"tma_rows", 7)
+        y, stats, ag = run()
+        lib.b200_set_option(b"tma_rows", 0)
+        y0, stats0, ag0 = run()
+    finally:
+        lib.b200_set_option(b"tma_rows", before)
+    assert_close(y, y_ref, atol=2e-5, rtol=2e-6, what="tma_rows y")
+    st = stats.sum(0)
+    ycpu = y.double().cpu()
+    mean = st[:cout] / n
+    var = st[cout:] / n - mean * mean
+    assert_close(mean, ycpu.mean(0), atol=0.0, rtol=1e-9, what="column means")
+    assert_close(var, ycpu.var(0, unbiased=False), atol=0.0, rtol=1e-6, what="column variances")
+    assert rel_err(ag[0].grad, ga_ref[:, :c1]) < 2e-6, rel_err(ag[0].grad, ga_ref[:, :c1])
+    if c2:
+        assert rel_err(ag[3].grad, ga_ref[:, c1:]) < 2e-6, rel_err(ag[3].grad, ga_ref[:, c1:])
+    assert rel_err(ag[1].grad, gw_ref) < 5e-6, rel_err(ag[1].grad, gw_ref)  # fp32 accumulation over n rows
+    assert rel_err(ag[2].grad, gb_ref) < 5e-6, rel_err(ag[2].grad, gb_ref)
+    # the kernels they stand in for agree to fp32 round-off (different summation orders)
+    assert rel_err(y, y0.double()) < 2e-6 and rel_err(ag[0].grad, ag0[0].grad.double()) < 2e-6
+    assert rel_err(ag[1].grad, ag0[1].grad.double()) < 1e-5
+    # one partial row per CTA, the remaining rows of the caller's buffer are exact zeros
+    assert stats.shape == stats0.shape
+    if n >= 204800:
+        assert float(stats[2 * 148:].abs().max()) == 0.0, "the TMA kernel did not run (partials beyond the grid are not zero)"
+
+
+def test_linear_tma_rows_kernels_run(lib):
+    """The option bits really select the TMA kernels (kernel names from CUPTI) and a null input-gradient pointer of
+    one segment is honoured."""
+    from myria3d_b200 import ops
+    from torch.profiler import ProfilerActivity, profile
+
+    g = torch.Generator().manual_seed(5)
+    n = 16384
+    a1, a2 = torch.randn(n, 32, generator=g).to(DEV), torch.randn(n, 32, generator=g).to(DEV).requires_grad_(True)
+    w = (torch.randn(32, 64, generator=g) / 8).to(DEV).requires_grad_(True)
+    b = torch.randn(32, generator=g).to(DEV).requires_grad_(True)
+    gy = torch.randn(n, 32, generator=g).to(DEV)
+    before = int(lib.b200_get_option(b"tma_rows"))
+    try:
+        lib.b200_set_option(b"tma_rows", 7)
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            ops.linear(a1, w, b, a2=a2).backward(gy)
+            torch.cuda.synchronize()
+    finally:
+        lib.b200_set_option(b"tma_rows", before)
+    names = " ".join(e.key for e in prof.key_averages())
+    assert names.count("tma_rows_nn_kernel") >= 1 and "tma_rows_tn_kernel" in names, names
+    ga_ref = gy.double() @ w.detach().double()
+    assert rel_err(a2.grad, ga_ref[:, 32:]) < 2e-6
+
+
 @pytest.mark.parametrize("n,c1,c2,cout,bias", [(204800, 32, 0, 4, True), (204800, 9, 0, 32, True), (204800, 32, 0, 33, True),
                                                (51200, 32, 0, 4, True), (60001, 17, 0, 32, True), (4096, 64, 0, 12, False),
                                                (204800, 32, 0, 64, True), (7777, 24, 8, 20, True)])
