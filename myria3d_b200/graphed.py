@@ -29,7 +29,7 @@ from typing import Dict, List, Optional, Tuple
 import torch
 from torch import Tensor
 
-from . import _lib
+from . import _lib, ops
 from .data import Batch
 
 
@@ -300,6 +300,7 @@ class GraphedTrainStep:
             for dst, src in zip(cap.idx_static, idx):
                 dst.copy_(src, non_blocking=True)
         cap.graph.replay()
+        ops.mark_scratch_dirty(self.device)  # the replay left its reduction sums in the scratch slices of the capture
         if cap.opt_graph is not None:
             self.reducer.all_reduce()
             cap.opt_graph.replay()

@@ -112,38 +112,62 @@ class _ScratchArena:
     """Zero-filled scratch for the small reduction buffers of the backward pass (BatchNorm sums, encoder gradients, loss
     accumulators): slices of one buffer that ``reset()`` clears with ONE memset at the start of the next forward instead
     of one fill kernel per buffer (~90 launches per training step).  A slice may only be handed to consumers that finish
-    within the same forward/backward pass; when the arena is full callers fall back to ``torch.zeros``."""
+    within the same forward/backward pass; when the arena is full callers fall back to ``torch.zeros``.
+
+    ``reset()`` clears everything that was EVER handed out (``hw``, the high-water mark), not just the last pass: the
+    replay of a captured step graph leaves its sums in the slices it was captured with, which may lie beyond the extent
+    of the pass that ran last from Python.  Replays are invisible from here, so ``GraphedTrainStep`` reports them
+    (``mark_scratch_dirty``) and the next eager ``take()`` clears the arena first -- callers that never go through
+    ``B200RandLANet.forward`` (a bare LocalFeatureAggregation, ``ops.cross_entropy``) stay correct after a replay."""
 
     def __init__(self, device: torch.device, nbytes: int = 1 << 20):
         self.buf = torch.zeros(nbytes, dtype=torch.uint8, device=device)
         self.off = 0
+        self.hw = 0
+        self.dirty = False
 
     def take(self, numel: int, dtype: torch.dtype) -> Optional[Tensor]:
+        if self.dirty and not torch.cuda.is_current_stream_capturing():
+            self.reset()
         nbytes = (numel * torch.empty((), dtype=dtype).element_size() + 15) // 16 * 16
         if self.off + nbytes > self.buf.numel():
             return None
         t = self.buf[self.off:self.off + nbytes].view(dtype)[:numel]
         self.off += nbytes
+        self.hw = max(self.hw, self.off)
         return t
 
     def reset(self) -> None:
-        if self.off:
-            self.buf[:self.off].zero_()
+        if self.hw:
+            self.buf[:self.hw].zero_()
         self.off = 0
+        if not torch.cuda.is_current_stream_capturing():
+            self.dirty = False
 
 
 _ARENAS: dict = {}
 
 
+def _arena_key(device: torch.device) -> int:
+    return device.index if device.index is not None else torch.cuda.current_device()
+
+
 def reset_scratch(device: torch.device) -> None:
     """Called by ``B200RandLANet.forward``: everything handed out since the last call is dead by now."""
-    a = _ARENAS.get(device.index if device.index is not None else torch.cuda.current_device())
+    a = _ARENAS.get(_arena_key(device))
     if a is not None:
         a.reset()
 
 
+def mark_scratch_dirty(device: torch.device) -> None:
+    """Called after the replay of a captured step graph: its kernels wrote into the arena slices of the capture."""
+    a = _ARENAS.get(_arena_key(device))
+    if a is not None:
+        a.dirty = True
+
+
 def _zeros_scratch(numel: int, dtype: torch.dtype, device: torch.device) -> Tensor:
-    key = device.index if device.index is not None else torch.cuda.current_device()
+    key = _arena_key(device)
     a = _ARENAS.get(key)
     if a is None:
         a = _ARENAS[key] = _ScratchArena(device)

@@ -295,3 +295,34 @@ def test_prefetch_feeds_the_next_replay(lib):
         step.prefetch(nxt)
         assert torch.isfinite(loss).item()
         assert torch.equal(cap.static["y"].cpu(), cur.y)
+
+
+def test_scratch_arena_is_clean_after_a_graph_replay(lib):
+    """The replay of a captured step leaves its reduction sums in the arena slices it was captured with -- possibly beyond
+    the extent of the pass that ran last from Python (another, smaller layout).  Consumers that never pass through
+    ``B200RandLANet.forward`` (a bare LocalFeatureAggregation, ``ops.cross_entropy``) must still be handed zeros: the
+    arena is cleared up to its high-water mark, and a reported replay makes the next eager ``take()`` clear it first
+    (found by running test_lfa_module_parity after the graph tests: fp64 sums read back as fp32 gave 1e27 gradients)."""
+    from myria3d_b200 import ops
+
+    dev = torch.device(DEV)
+    ops._zeros_scratch(8, torch.float32, dev)  # make sure the arena exists
+    arena = ops._ARENAS[ops._arena_key(dev)]
+    ops.reset_scratch(dev)
+    big = ops._zeros_scratch(5000, torch.float64, dev)  # the extent of a large captured layout ...
+    ops.reset_scratch(dev)
+    small = ops._zeros_scratch(16, torch.float32, dev)  # ... then a small pass: Python's offset is far below it
+    assert arena.off < arena.hw
+    big.fill_(70.245)  # what a replay of the large graph leaves behind
+    ops.mark_scratch_dirty(dev)
+    t = ops._zeros_scratch(64, torch.float32, dev)
+    u = ops._zeros_scratch(3000, torch.float64, dev)
+    torch.cuda.synchronize()
+    assert float(t.abs().max()) == 0.0 and float(u.abs().max()) == 0.0
+    assert not arena.dirty
+    # reset() always clears up to the high-water mark
+    u.fill_(1.0)
+    ops.reset_scratch(dev)
+    v = ops._zeros_scratch(5000, torch.float64, dev)
+    assert float(v.abs().max()) == 0.0
+    del small
