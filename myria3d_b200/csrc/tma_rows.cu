@@ -107,10 +107,6 @@ tma_rows_nn_kernel(const __grid_constant__ CUtensorMap map0, const __grid_consta
   const int tid = threadIdx.x;
   const int cg = tid % C::NCG, rg = tid / C::NCG;
 
-  for (int t = tid; t < C::KP * MP; t += TR_THREADS) {
-    const int k = t / MP, m = t % MP;
-    Bs[t] = w_out_major ? __ldg(w + (int64_t)m * w_ld + k) : __ldg(w + (int64_t)k * w_ld + m);
-  }
   if (tid == 0) {
     for (int s = 0; s < C::STAGES; ++s) mbar_init(&full[s], 1);
     mbar_fence_init();
@@ -129,15 +125,32 @@ tma_rows_nn_kernel(const __grid_constant__ CUtensorMap map0, const __grid_consta
     tma_load_2d(dst, pm0, 0, row0, bar);
     if constexpr (NSUB == 2) tma_load_2d(dst + C::SUB_BYTES, pm1, col1, row0, bar);
   };
+  // the first tiles are on their way while the weights are staged (ncu, round 2: the two latencies in sequence were a
+  // fifth of the kernel)
   if (tid == 0)
     for (int i = 0; i < C::STAGES && i < my_tiles; ++i) issue(i);
+  for (int t = tid; t < C::KP * MP; t += TR_THREADS) {  // Bs[k][m]; global reads coalesced in both orientations
+    if (w_out_major) {
+      const int m = t / C::KP, k = t % C::KP;
+      Bs[k * MP + m] = __ldg(w + (int64_t)m * w_ld + k);
+    } else {
+      Bs[t] = __ldg(w + (int64_t)(t / MP) * w_ld + (t % MP));
+    }
+  }
+  __syncthreads();
 
   float bv[4] = {0.f, 0.f, 0.f, 0.f};
   if (bias) {
 #pragma unroll
     for (int u = 0; u < 4; ++u) bv[u] = __ldg(bias + cg * 4 + u);
   }
-  double ps[4] = {0.0, 0.0, 0.0, 0.0}, pq[4] = {0.0, 0.0, 0.0, 0.0};
+  // BatchNorm statistics: per thread and column, sum and sum of squares of d = v - pivot in fp32, pivot = the thread's
+  // first output of that column.  A thread sees <= a few dozen rows, |d| is of the order of the column's spread, so the
+  // fp32 sums carry no cancellation (|mean| >> std lives in the pivot); the fp64 totals are rebuilt once at the end:
+  // sum v = cnt * pivot + sum d, sum v^2 = sum d^2 + 2 pivot sum d + cnt pivot^2.  (Round 2 first version: fp64 per
+  // element -- the F2F.F64.F32 conversions kept the XU pipe 48 % busy, ncu.)
+  float pc[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+  int cnt = 0;
   const int col = cg * 4;
   float* const obase = (col < oc1) ? (o1 ? o1 + col : nullptr) : (o2 ? o2 + (col - oc1) : nullptr);
   const int64_t old = (col < oc1) ? old1 : old2;
@@ -185,16 +198,29 @@ tma_rows_nn_kernel(const __grid_constant__ CUtensorMap map0, const __grid_consta
       for (int u = 0; u < 4; ++u) v[u] = acc[r][u] + bv[u];
       if (obase) *reinterpret_cast<float4*>(obase + row * old) = make_float4(v[0], v[1], v[2], v[3]);
       if (colstats) {
+        if (cnt == 0) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) pc[u] = v[u];
+        }
+        ++cnt;
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          ps[u] += (double)v[u];
-          pq[u] = fma((double)v[u], (double)v[u], pq[u]);
+          const float d = v[u] - pc[u];
+          s1[u] += d;
+          s2[u] = fmaf(d, d, s2[u]);
         }
       }
     }
   }
 
   if (colstats) {
+    double ps[4], pq[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const double p = (double)pc[u], a = (double)s1[u], n_ = (double)cnt;
+      ps[u] = fma(n_, p, a);
+      pq[u] = (double)s2[u] + p * (2.0 * a + n_ * p);
+    }
     // lanes of a warp with the same column group differ in lane bits >= log2(NCG)
 #pragma unroll
     for (int off = C::NCG; off < 32; off <<= 1) {
@@ -260,11 +286,11 @@ tma_rows_tn_kernel(const __grid_constant__ CUtensorMap mapx0, const __grid_const
   const int bid = tid % C::NBLK, rq = tid / C::NBLK;
   const int kb = bid % C::NKB, mb = bid / C::NKB;
 
-  for (int t = tid; t < MP * C::KP + MP; t += TR_THREADS) R[t] = 0.f;
   if (tid == 0) {
     for (int s = 0; s < C::STAGES; ++s) mbar_init(&full[s], 1);
     mbar_fence_init();
   }
+  for (int t = tid; t < MP * C::KP + MP; t += TR_THREADS) R[t] = 0.f;
   __syncthreads();
 
   const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;

@@ -127,7 +127,7 @@ class _ScratchArena:
         self.dirty = False
 
     def take(self, numel: int, dtype: torch.dtype) -> Optional[Tensor]:
-        if self.dirty and not torch.cuda.is_current_stream_capturing():
+        if self.dirty and not self._capturing():
             self.reset()
         nbytes = (numel * torch.empty((), dtype=dtype).element_size() + 15) // 16 * 16
         if self.off + nbytes > self.buf.numel():
@@ -141,8 +141,11 @@ class _ScratchArena:
         if self.hw:
             self.buf[:self.hw].zero_()
         self.off = 0
-        if not torch.cuda.is_current_stream_capturing():
+        if not self._capturing():
             self.dirty = False
+
+    def _capturing(self) -> bool:
+        return self.buf.is_cuda and torch.cuda.is_current_stream_capturing()
 
 
 _ARENAS: dict = {}
