@@ -700,47 +700,28 @@ affine_act_bwd_reduce_vec4_kernel(const float* __restrict__ go, const float* __r
       if (y2) m2 = __ldg(reinterpret_cast<const float4*>(mean2) + q), is2 = __ldg(reinterpret_cast<const float4*>(invstd2) + q);
       const float m1a[4] = {m1.x, m1.y, m1.z, m1.w}, i1a[4] = {is1.x, is1.y, is1.z, is1.w};
       const float m2a[4] = {m2.x, m2.y, m2.z, m2.w}, i2a[4] = {is2.x, is2.y, is2.z, is2.w};
-      // two rows per iteration: 6-8 independent 16-byte loads in flight per thread (4 CTAs x 256 threads x 3 loads were
-      // 48 KB per SM, just the bandwidth-delay product of HBM3e: 2.5 TB/s)
-      const int64_t stride = (int64_t)gridDim.x * rstep;
-      for (int64_t i = (int64_t)blockIdx.x * rstep + rsub; i < n; i += 2 * stride) {
-        const bool two = i + stride < n;
-        const int64_t off0 = i * c4 + q, off1 = (two ? i + stride : i) * c4 + q;
-        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        float4 gq[2], aq[2], oq[2], bq[2];
-        gq[0] = __ldg(reinterpret_cast<const float4*>(go) + off0);
-        aq[0] = __ldg(reinterpret_cast<const float4*>(y1) + off0);
-        gq[1] = two ? __ldg(reinterpret_cast<const float4*>(go) + off1) : z4;  // g = 0: the row adds nothing
-        aq[1] = __ldg(reinterpret_cast<const float4*>(y1) + off1);
-        oq[0] = oq[1] = make_float4(1.f, 1.f, 1.f, 1.f);
+      for (int64_t i = (int64_t)blockIdx.x * rstep + rsub; i < n; i += (int64_t)gridDim.x * rstep) {
+        const int64_t off = i * c4 + q;
+        const float4 g4 = __ldg(reinterpret_cast<const float4*>(go) + off);
+        const float4 a4 = __ldg(reinterpret_cast<const float4*>(y1) + off);
+        float g[4] = {g4.x, g4.y, g4.z, g4.w};
+        const float a[4] = {a4.x, a4.y, a4.z, a4.w};
         if (slope != 1.f) {
-          oq[0] = __ldg(reinterpret_cast<const float4*>(out) + off0);
-          oq[1] = __ldg(reinterpret_cast<const float4*>(out) + off1);
+          const float4 o4 = __ldg(reinterpret_cast<const float4*>(out) + off);
+          const float o[4] = {o4.x, o4.y, o4.z, o4.w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) g[u] *= (o[u] > 0.f) ? 1.f : slope;
         }
-        bq[0] = bq[1] = z4;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          sg[u] += g[u];
+          sx1[u] = fmaf(g[u], (a[u] - m1a[u]) * i1a[u], sx1[u]);
+        }
         if (y2) {
-          bq[0] = __ldg(reinterpret_cast<const float4*>(y2) + off0);
-          bq[1] = __ldg(reinterpret_cast<const float4*>(y2) + off1);
-        }
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(y2) + off);
+          const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          float g[4] = {gq[h].x, gq[h].y, gq[h].z, gq[h].w};
-          const float a[4] = {aq[h].x, aq[h].y, aq[h].z, aq[h].w};
-          const float o[4] = {oq[h].x, oq[h].y, oq[h].z, oq[h].w};
-          const float bb[4] = {bq[h].x, bq[h].y, bq[h].z, bq[h].w};
-          if (slope != 1.f) {
-#pragma unroll
-            for (int u = 0; u < 4; ++u) g[u] *= (o[u] > 0.f) ? 1.f : slope;
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            sg[u] += g[u];
-            sx1[u] = fmaf(g[u], (a[u] - m1a[u]) * i1a[u], sx1[u]);
-          }
-          if (y2) {
-#pragma unroll
-            for (int u = 0; u < 4; ++u) sx2[u] = fmaf(g[u], (bb[u] - m2a[u]) * i2a[u], sx2[u]);
-          }
+          for (int u = 0; u < 4; ++u) sx2[u] = fmaf(g[u], (bb[u] - m2a[u]) * i2a[u], sx2[u]);
         }
       }
     }
