@@ -325,14 +325,16 @@ __device__ __forceinline__ void centre_gemm(float (&acc)[Cfg::KT][Cfg::CW], cons
 #pragma unroll
       for (int k = 0; k < KT; ++k) {
         const float4 a = *reinterpret_cast<const float4*>(A + k * C + r);
+        // packed FMAs over column pairs (FFMA2): same products, same accumulation order per column as the scalar loop
+        const float2 ax = make_float2(a.x, a.x), ay = make_float2(a.y, a.y), az = make_float2(a.z, a.z), aw = make_float2(a.w, a.w);
 #pragma unroll
-        for (int cw = 0; cw < CW; ++cw) {
-          float v = acc[k][cw];
-          v = fmaf(a.x, b[half][0][cw], v);
-          v = fmaf(a.y, b[half][1][cw], v);
-          v = fmaf(a.z, b[half][2][cw], v);
-          v = fmaf(a.w, b[half][3][cw], v);
-          acc[k][cw] = v;
+        for (int cw = 0; cw < CW; cw += 2) {
+          float2 v = make_float2(acc[k][cw], acc[k][cw + 1]);
+          v = ffma2(ax, make_float2(b[half][0][cw], b[half][0][cw + 1]), v);
+          v = ffma2(ay, make_float2(b[half][1][cw], b[half][1][cw + 1]), v);
+          v = ffma2(az, make_float2(b[half][2][cw], b[half][2][cw + 1]), v);
+          v = ffma2(aw, make_float2(b[half][3][cw], b[half][3][cw + 1]), v);
+          acc[k][cw] = v.x, acc[k][cw + 1] = v.y;
         }
       }
     }
@@ -565,10 +567,8 @@ lfa_bwd_kernel(const float* __restrict__ x, const float* __restrict__ pos, const
               const float4 fr = *reinterpret_cast<const float4*>(Fg + k * C + m4 * 4);  // broadcast within the centre
 #pragma unroll
               for (int cw = 0; cw < CW; ++cw) {
-                dwc[cw][m4 * 4 + 0] = fmaf(da[cw], fr.x, dwc[cw][m4 * 4 + 0]);
-                dwc[cw][m4 * 4 + 1] = fmaf(da[cw], fr.y, dwc[cw][m4 * 4 + 1]);
-                dwc[cw][m4 * 4 + 2] = fmaf(da[cw], fr.z, dwc[cw][m4 * 4 + 2]);
-                dwc[cw][m4 * 4 + 3] = fmaf(da[cw], fr.w, dwc[cw][m4 * 4 + 3]);
+                ffma2_bc(da[cw], fr.x, fr.y, dwc[cw][m4 * 4 + 0], dwc[cw][m4 * 4 + 1]);
+                ffma2_bc(da[cw], fr.z, fr.w, dwc[cw][m4 * 4 + 2], dwc[cw][m4 * 4 + 3]);
               }
             }
           }
@@ -656,9 +656,10 @@ lfa_bwd_kernel(const float* __restrict__ x, const float* __restrict__ pos, const
           const float av[4] = {a.x, a.y, a.z, a.w};
           const float bv[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-          for (int r = 0; r < 4; ++r)
-#pragma unroll
-            for (int s = 0; s < 4; ++s) dw[pass][r * 4 + s] = fmaf(av[r], bv[s], dw[pass][r * 4 + s]);
+          for (int r = 0; r < 4; ++r) {
+            ffma2_bc(av[r], bv[0], bv[1], dw[pass][r * 4 + 0], dw[pass][r * 4 + 1]);
+            ffma2_bc(av[r], bv[2], bv[3], dw[pass][r * 4 + 2], dw[pass][r * 4 + 3]);
+          }
         }
       }
     }

@@ -105,10 +105,8 @@ linear_rows_kernel(LrIn X, const float* __restrict__ w, int w_ld, bool w_out_maj
 #pragma unroll
       for (int c = 0; c < CO; c += 4) {
         const float4 w4 = *reinterpret_cast<const float4*>(&Ws[k][c]);
-        acc[c] = fmaf(xk, w4.x, acc[c]);
-        acc[c + 1] = fmaf(xk, w4.y, acc[c + 1]);
-        acc[c + 2] = fmaf(xk, w4.z, acc[c + 2]);
-        acc[c + 3] = fmaf(xk, w4.w, acc[c + 3]);
+        ffma2_bc(xk, w4.x, w4.y, acc[c], acc[c + 1]);  // FFMA2: the row's input in the broadcast slot
+        ffma2_bc(xk, w4.z, w4.w, acc[c + 2], acc[c + 3]);
       }
     }
     if (valid) {

@@ -67,7 +67,7 @@ static CatRows make_cat(const float* a1, int64_t ld1, int c1, const float* a2, i
 template <int BM, int BN>
 struct GemmTile {
   static constexpr int TM = BM / 16, TN = BN / 16;
-  static_assert(BM % 16 == 0 && BN % 16 == 0, "tile");
+  static_assert(BM % 16 == 0 && BN % 32 == 0, "tile (column pairs per thread)");
   float acc[TM][TN];
   __device__ __forceinline__ void zero() {
 #pragma unroll
@@ -87,7 +87,7 @@ struct GemmTile {
 #pragma unroll
       for (int r = 0; r < TM; ++r)
 #pragma unroll
-        for (int s = 0; s < TN; ++s) acc[r][s] = fmaf(a[r], b[s], acc[r][s]);
+        for (int s = 0; s < TN; s += 2) ffma2_bc(a[r], b[s], b[s + 1], acc[r][s], acc[r][s + 1]);  // FFMA2, same order
     }
   }
 };
@@ -434,15 +434,24 @@ tn_skinny_kernel(const float* __restrict__ gy, int cout, CatRows A, float* __res
 #pragma unroll
       for (int c4 = 0; c4 < CO / 4; ++c4) {
         const float4 g = *reinterpret_cast<const float4*>(GY + row * CO + c4 * 4);
-        acc0[c4 * 4 + 0] = fmaf(g.x, a0, acc0[c4 * 4 + 0]);
-        acc0[c4 * 4 + 1] = fmaf(g.y, a0, acc0[c4 * 4 + 1]);
-        acc0[c4 * 4 + 2] = fmaf(g.z, a0, acc0[c4 * 4 + 2]);
-        acc0[c4 * 4 + 3] = fmaf(g.w, a0, acc0[c4 * 4 + 3]);
-        if (TWO) {
-          acc1[c4 * 4 + 0] = fmaf(g.x, a1, acc1[c4 * 4 + 0]);
-          acc1[c4 * 4 + 1] = fmaf(g.y, a1, acc1[c4 * 4 + 1]);
-          acc1[c4 * 4 + 2] = fmaf(g.z, a1, acc1[c4 * 4 + 2]);
-          acc1[c4 * 4 + 3] = fmaf(g.w, a1, acc1[c4 * 4 + 3]);
+        if constexpr (CO * (TWO ? 2 : 1) <= 64) {  // FFMA2: the activation in the broadcast slot
+          ffma2_bc(a0, g.x, g.y, acc0[c4 * 4 + 0], acc0[c4 * 4 + 1]);
+          ffma2_bc(a0, g.z, g.w, acc0[c4 * 4 + 2], acc0[c4 * 4 + 3]);
+          if (TWO) {
+            ffma2_bc(a1, g.x, g.y, acc1[c4 * 4 + 0], acc1[c4 * 4 + 1]);
+            ffma2_bc(a1, g.z, g.w, acc1[c4 * 4 + 2], acc1[c4 * 4 + 3]);
+          }
+        } else {  // 128 accumulators: the even-aligned register pairs of the packed form would spill
+          acc0[c4 * 4 + 0] = fmaf(g.x, a0, acc0[c4 * 4 + 0]);
+          acc0[c4 * 4 + 1] = fmaf(g.y, a0, acc0[c4 * 4 + 1]);
+          acc0[c4 * 4 + 2] = fmaf(g.z, a0, acc0[c4 * 4 + 2]);
+          acc0[c4 * 4 + 3] = fmaf(g.w, a0, acc0[c4 * 4 + 3]);
+          if (TWO) {
+            acc1[c4 * 4 + 0] = fmaf(g.x, a1, acc1[c4 * 4 + 0]);
+            acc1[c4 * 4 + 1] = fmaf(g.y, a1, acc1[c4 * 4 + 1]);
+            acc1[c4 * 4 + 2] = fmaf(g.z, a1, acc1[c4 * 4 + 2]);
+            acc1[c4 * 4 + 3] = fmaf(g.w, a1, acc1[c4 * 4 + 3]);
+          }
         }
       }
     }

@@ -170,14 +170,12 @@ tma_rows_nn_kernel(const __grid_constant__ CUtensorMap map0, const __grid_consta
 #pragma unroll
         for (int r = 0; r < C::TR; ++r) {
           const float4 a = *reinterpret_cast<const float4*>(T + sw_off<WS>(r * C::NRG + rg, j));
-          acc[r][0] = fmaf(a.x, b[0].x, acc[r][0]), acc[r][1] = fmaf(a.x, b[0].y, acc[r][1]);
-          acc[r][2] = fmaf(a.x, b[0].z, acc[r][2]), acc[r][3] = fmaf(a.x, b[0].w, acc[r][3]);
-          acc[r][0] = fmaf(a.y, b[1].x, acc[r][0]), acc[r][1] = fmaf(a.y, b[1].y, acc[r][1]);
-          acc[r][2] = fmaf(a.y, b[1].z, acc[r][2]), acc[r][3] = fmaf(a.y, b[1].w, acc[r][3]);
-          acc[r][0] = fmaf(a.z, b[2].x, acc[r][0]), acc[r][1] = fmaf(a.z, b[2].y, acc[r][1]);
-          acc[r][2] = fmaf(a.z, b[2].z, acc[r][2]), acc[r][3] = fmaf(a.z, b[2].w, acc[r][3]);
-          acc[r][0] = fmaf(a.w, b[3].x, acc[r][0]), acc[r][1] = fmaf(a.w, b[3].y, acc[r][1]);
-          acc[r][2] = fmaf(a.w, b[3].z, acc[r][2]), acc[r][3] = fmaf(a.w, b[3].w, acc[r][3]);
+          // packed FMAs (FFMA2) over column pairs, the row value in the broadcast slot: half the issue slots and half the
+          // FMA-pipe cycles of 16 scalar FFMAs (the scalar form issues every second cycle on sm_100a)
+          ffma2_bc(a.x, b[0].x, b[0].y, acc[r][0], acc[r][1]), ffma2_bc(a.x, b[0].z, b[0].w, acc[r][2], acc[r][3]);
+          ffma2_bc(a.y, b[1].x, b[1].y, acc[r][0], acc[r][1]), ffma2_bc(a.y, b[1].z, b[1].w, acc[r][2], acc[r][3]);
+          ffma2_bc(a.z, b[2].x, b[2].y, acc[r][0], acc[r][1]), ffma2_bc(a.z, b[2].z, b[2].w, acc[r][2], acc[r][3]);
+          ffma2_bc(a.w, b[3].x, b[3].y, acc[r][0], acc[r][1]), ffma2_bc(a.w, b[3].z, b[3].w, acc[r][2], acc[r][3]);
         }
       }
     }
@@ -319,14 +317,10 @@ tma_rows_tn_kernel(const __grid_constant__ CUtensorMap mapx0, const __grid_const
       const int row = rq * C::RPT + rr;
       const float4 x = *reinterpret_cast<const float4*>(X + sw_off<WS>(row, xchunk));
       const float4 g = *reinterpret_cast<const float4*>(G + sw_off<C::GWS>(row, gchunk));
-      acc[0][0] = fmaf(g.x, x.x, acc[0][0]), acc[0][1] = fmaf(g.x, x.y, acc[0][1]);
-      acc[0][2] = fmaf(g.x, x.z, acc[0][2]), acc[0][3] = fmaf(g.x, x.w, acc[0][3]);
-      acc[1][0] = fmaf(g.y, x.x, acc[1][0]), acc[1][1] = fmaf(g.y, x.y, acc[1][1]);
-      acc[1][2] = fmaf(g.y, x.z, acc[1][2]), acc[1][3] = fmaf(g.y, x.w, acc[1][3]);
-      acc[2][0] = fmaf(g.z, x.x, acc[2][0]), acc[2][1] = fmaf(g.z, x.y, acc[2][1]);
-      acc[2][2] = fmaf(g.z, x.z, acc[2][2]), acc[2][3] = fmaf(g.z, x.w, acc[2][3]);
-      acc[3][0] = fmaf(g.w, x.x, acc[3][0]), acc[3][1] = fmaf(g.w, x.y, acc[3][1]);
-      acc[3][2] = fmaf(g.w, x.z, acc[3][2]), acc[3][3] = fmaf(g.w, x.w, acc[3][3]);
+      ffma2_bc(g.x, x.x, x.y, acc[0][0], acc[0][1]), ffma2_bc(g.x, x.z, x.w, acc[0][2], acc[0][3]);
+      ffma2_bc(g.y, x.x, x.y, acc[1][0], acc[1][1]), ffma2_bc(g.y, x.z, x.w, acc[1][2], acc[1][3]);
+      ffma2_bc(g.z, x.x, x.y, acc[2][0], acc[2][1]), ffma2_bc(g.z, x.z, x.w, acc[2][2], acc[2][3]);
+      ffma2_bc(g.w, x.x, x.y, acc[3][0], acc[3][1]), ffma2_bc(g.w, x.z, x.w, acc[3][2], acc[3][3]);
       if (kb == 0) bs[0] += g.x, bs[1] += g.y, bs[2] += g.z, bs[3] += g.w;
     }
     __syncthreads();
