@@ -219,6 +219,44 @@ def algorithmic_flops(name: str, a):
     return 0
 
 
+def make_roofline(table, clocks, dev, args, ms_per_step):
+    """The `roofline` object of the bench line from the per-kernel table (dominant library call first)."""
+    import torch
+
+    peak, peak_src = peaks()
+    roof = None
+    if table:
+        top = table[0]
+        lib_ms = sum(g["ms"] for g in table)
+        traffic, traffic_src = ncu_traffic(top["name"], tuple(top["args"]))
+        flops = algorithmic_flops(top["name"], tuple(top["args"]))
+        sm_max = (clocks or {}).get("sm_max_mhz") or 1965
+        fma_peak = torch.cuda.get_device_properties(dev).multi_processor_count * 128 * 2 * sm_max * 1e6 / 1e12
+        tfs = flops / (top["ms_per_launch"] * 1e-3) / 1e12
+        roof = {"bound": "hbm", "kernel": top["name"], "kernel_args": top["args"],
+                "achieved": top["gbs"], "peak": peak, "unit": "GB/s", "frac": top["gbs"] / peak,
+                "traffic": traffic, "traffic_source": traffic_src,
+                # the same launch against the fp32 FMA pipe (SMs x 128 lanes x 2 x max clock): the fused LFA kernels are
+                # ALU-bound long before they are HBM-bound (DESIGN.md section 6)
+                "fp32_fma": {"flops": flops, "achieved": tfs, "peak": fma_peak, "unit": "TFLOP/s",
+                             "frac": tfs / fma_peak if fma_peak else None},
+                "peak_source": peak_src, "launch_ms": top["ms_per_launch"],
+                "share_of_library_time": top["ms"] / lib_ms if lib_ms > 0 else None,
+                "library_ms_per_step": lib_ms,
+                # the next library calls by time, same definition of `achieved` (algorithmic bytes / CUDA-event time)
+                "also": [{"kernel": g["name"], "kernel_args": g["args"], "launch_ms": g["ms_per_launch"],
+                          "achieved": g["gbs"], "frac": g["gbs"] / peak,
+                          "traffic": ncu_traffic(g["name"], tuple(g["args"]))[0]}
+                         for g in table[1:9] if g["alg_bytes"] > 0]}
+        report = args.kernel_report
+        if report is None and os.path.isdir(os.path.join(ROOT, "gpurun_out")):
+            report = os.path.join(ROOT, "gpurun_out", "bench_kernels.json")
+        if report:
+            with open(report, "w") as f:
+                json.dump({"ms_per_step": ms_per_step, "kernels": table}, f, indent=1)
+    return roof
+
+
 def ncu_traffic(name: str, a):
     """dram bytes per launch of this kernel/shape from the committed single-kernel ncu capture, else None."""
     try:
@@ -528,6 +566,18 @@ def run_b200_predict(args):
         dist.barrier()
     e2e_ms = max_over_ranks(timed("e2e", args.steps))
     clocks = sampler.stop() if rank == 0 else None
+    table = []
+    if rank == 0 and args.profile_steps > 0:  # per-kernel pass (CUDA events around every library call) for `roofline`
+        prof = _lib.KernelProfiler()
+        _lib.PROFILER = prof
+        for s in range(args.profile_steps):
+            step(resident[s % n_rot])
+        _lib.PROFILER = None
+        torch.cuda.synchronize()
+        table = kernel_table([(n, i, ms_ / 1.0) for n, i, ms_ in prof.summary()])
+        for g in table:
+            g["ms"] /= args.profile_steps
+            g["launches"] //= args.profile_steps
     if rank == 0:
         pts = args.tiles * FULL_POINTS
         ms = total_ms / args.steps
@@ -543,7 +593,7 @@ def run_b200_predict(args):
                 "gpu_launches": int(launches),
                 "e2e": {"value": pts * world / (e2e_ms / args.steps * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                         "d2h_bytes_per_step": int(out_host.numel() * 8), "ms_per_step": e2e_ms / args.steps},
-                "roofline": None, "cpu_baseline": cpu}
+                "roofline": make_roofline(table, clocks, dev, args, ms), "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -703,37 +753,7 @@ def run_b200(args):
         ms_per_step = total_ms / args.steps
         value = points_per_step * world / (ms_per_step * 1e-3)
         e2e_val = points_per_step * world / (e2e_ms / args.steps * 1e-3)
-        peak, peak_src = peaks()
-        roof = None
-        if table:
-            top = table[0]
-            lib_ms = sum(g["ms"] for g in table)
-            traffic, traffic_src = ncu_traffic(top["name"], tuple(top["args"]))
-            flops = algorithmic_flops(top["name"], tuple(top["args"]))
-            sm_max = (clocks or {}).get("sm_max_mhz") or 1965
-            fma_peak = torch.cuda.get_device_properties(dev).multi_processor_count * 128 * 2 * sm_max * 1e6 / 1e12
-            tfs = flops / (top["ms_per_launch"] * 1e-3) / 1e12
-            roof = {"bound": "hbm", "kernel": top["name"], "kernel_args": top["args"],
-                    "achieved": top["gbs"], "peak": peak, "unit": "GB/s", "frac": top["gbs"] / peak,
-                    "traffic": traffic, "traffic_source": traffic_src,
-                    # the same launch against the fp32 FMA pipe (SMs x 128 lanes x 2 x max clock): the fused LFA kernels are
-                    # ALU-bound long before they are HBM-bound
-                    "fp32_fma": {"flops": flops, "achieved": tfs, "peak": fma_peak, "unit": "TFLOP/s",
-                                 "frac": tfs / fma_peak if fma_peak else None},
-                    "peak_source": peak_src, "launch_ms": top["ms_per_launch"],
-                    "share_of_library_time": top["ms"] / lib_ms if lib_ms > 0 else None,
-                    "library_ms_per_step": lib_ms,
-                    # the next library calls by time, same definition of `achieved` (algorithmic bytes / CUDA-event time)
-                    "also": [{"kernel": g["name"], "kernel_args": g["args"], "launch_ms": g["ms_per_launch"],
-                              "achieved": g["gbs"], "frac": g["gbs"] / peak,
-                              "traffic": ncu_traffic(g["name"], tuple(g["args"]))[0]}
-                             for g in table[1:9] if g["alg_bytes"] > 0]}
-            report = args.kernel_report
-            if report is None and os.path.isdir(os.path.join(ROOT, "gpurun_out")):
-                report = os.path.join(ROOT, "gpurun_out", "bench_kernels.json")
-            if report:
-                with open(report, "w") as f:
-                    json.dump({"ms_per_step": ms_per_step, "kernels": table}, f, indent=1)
+        roof = make_roofline(table, clocks, dev, args, ms_per_step)
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             res = cpu_reference(args.cpu_tiles, args.points, args.cpu_steps, 2)
