@@ -48,12 +48,12 @@ EncodeTiledFn encode_fn() {
 }
 
 // rows x cols fp32 matrix with row stride ld (floats); box = TR_ROWS rows x ws columns, swizzle of the box width
-bool make_map(CUtensorMap* m, const float* base, int64_t ld, int cols, int64_t n, int ws) {
+bool make_map(CUtensorMap* m, const float* base, int64_t ld, int cols, int64_t n, int ws, int rows = TR_ROWS) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return false;
   const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)n};
   const cuuint64_t gstr[1] = {(cuuint64_t)ld * sizeof(float)};
-  const cuuint32_t box[2] = {(cuuint32_t)ws, (cuuint32_t)TR_ROWS};
+  const cuuint32_t box[2] = {(cuuint32_t)ws, (cuuint32_t)rows};
   const cuuint32_t estr[2] = {1, 1};
   const CUtensorMapSwizzle sw = ws == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr,
@@ -235,29 +235,40 @@ tma_rows_nn_kernel(const __grid_constant__ CUtensorMap map0, const __grid_consta
 }
 
 // ------------------------------------------------------------------ gw += gy^T [x0 | x1], gb += colsum(gy)
-template <int WS, int NSUB, int MP>
+// X rows: NS0 boxes of WS columns from map 0 (columns 0, WS, 2 WS, ...) followed by NS1 boxes from map 1 (the second
+// segment of a concatenated input, or nothing); gy rows: MP columns in boxes of <= 32.  ROWS = box height (64 for the
+// wide shapes, so that three to four stages fit).  A thread owns a 4 (m) x 4 KPT (k) block of gw for one slice of rows.
+template <int WS, int NS0, int NS1, int MP, int ROWS>
 struct TnCfg {
+  static constexpr int NSUB = NS0 + NS1;
   static constexpr int KP = WS * NSUB;
   static constexpr int GWS = MP >= 32 ? 32 : MP;  // box width of the gy tile
   static constexpr int MSUB = MP / GWS;
-  static constexpr int XSUB_BYTES = TR_ROWS * WS * 4;
-  static constexpr int GSUB_BYTES = TR_ROWS * GWS * 4;
+  static constexpr int XSUB_BYTES = ROWS * WS * 4;
+  static constexpr int GSUB_BYTES = ROWS * GWS * 4;
   static constexpr int STAGE_BYTES = NSUB * XSUB_BYTES + MSUB * GSUB_BYTES;
-  static constexpr int STAGES = STAGE_BYTES > 48 * 1024 ? 3 : (STAGE_BYTES >= 32 * 1024 ? 3 : 4);
+  static constexpr int STAGES = STAGE_BYTES >= 32 * 1024 ? 3 : 4;
   static constexpr int MINB = STAGE_BYTES > 32 * 1024 ? 1 : 2;
-  static constexpr int NKB = KP / 4, NMB = MP / 4, NBLK = NKB * NMB;  // 4 x 4 blocks of gw
-  static constexpr int RQ = TR_THREADS / NBLK;                           // row slices per tile
-  static constexpr int RPT = TR_ROWS / RQ;                               // rows per thread and tile
+  static constexpr int NKB = KP / 4, NMB = MP / 4;
+  static constexpr int KPT = (NKB * NMB > TR_THREADS) ? (NKB * NMB / TR_THREADS) : 1;  // 4-column groups per thread
+  static constexpr int NKG = NKB / KPT;                                              // k groups (of 4 KPT columns)
+  static constexpr int NBLK = NKG * NMB;
+  static constexpr int RQ = TR_THREADS / NBLK;  // row slices per tile
+  static constexpr int RPT = ROWS / RQ;         // rows per thread and tile
   static constexpr size_t SMEM = 1024 + (size_t)STAGES * STAGE_BYTES + (size_t)(MP * KP + MP) * 4 + STAGES * 8;
-  static_assert(NBLK <= TR_THREADS && RQ >= 1, "block map");
+  static_assert(NBLK <= TR_THREADS && RQ >= 1 && RQ * NBLK == TR_THREADS && RPT >= 1 && RPT * RQ == ROWS, "block map");
+  static_assert(KPT == 1 || KPT == 2, "a thread owns 4 or 8 columns of gw");
+  static_assert(KPT == 1 || (WS / 4) % KPT == 0, "a thread's columns stay inside one box");
+  static_assert(XSUB_BYTES % 1024 == 0 && GSUB_BYTES % 1024 == 0, "swizzle atoms");
+  static_assert(SMEM <= 232448, "shared memory");
 };
 
-template <int WS, int NSUB, int MP>
-__global__ void __launch_bounds__(TR_THREADS, TnCfg<WS, NSUB, MP>::MINB)
-tma_rows_tn_kernel(const __grid_constant__ CUtensorMap mapx0, const __grid_constant__ CUtensorMap mapx1, int colx1,
+template <int WS, int NS0, int NS1, int MP, int ROWS>
+__global__ void __launch_bounds__(TR_THREADS, TnCfg<WS, NS0, NS1, MP, ROWS>::MINB)
+tma_rows_tn_kernel(const __grid_constant__ CUtensorMap mapx0, const __grid_constant__ CUtensorMap mapx1,
                    const __grid_constant__ CUtensorMap mapg, float* __restrict__ gw, int gw_ld, float* __restrict__ gb,
                    int ntiles) {
-  using C = TnCfg<WS, NSUB, MP>;
+  using C = TnCfg<WS, NS0, NS1, MP, ROWS>;
   extern __shared__ uint8_t tr_smem_raw[];
   const uint32_t raw = smem_u32(tr_smem_raw);
   uint8_t* base = tr_smem_raw + ((1024u - (raw & 1023u)) & 1023u);
@@ -265,7 +276,7 @@ tma_rows_tn_kernel(const __grid_constant__ CUtensorMap mapx0, const __grid_const
   uint64_t* full = reinterpret_cast<uint64_t*>(R + MP * C::KP + MP);
   const int tid = threadIdx.x;
   const int bid = tid % C::NBLK, rq = tid / C::NBLK;
-  const int kb = bid % C::NKB, mb = bid / C::NKB;
+  const int kg = bid % C::NKG, mb = bid / C::NKG;
 
   if (tid == 0) {
     for (int s = 0; s < C::STAGES; ++s) mbar_init(&full[s], 1);
@@ -280,48 +291,53 @@ tma_rows_tn_kernel(const __grid_constant__ CUtensorMap mapx0, const __grid_const
   const CUtensorMap* const pmg = &mapg;
   auto issue = [&, pm0, pm1, pmg](int i) {
     const int s = i % C::STAGES;
-    const int row0 = ((int)blockIdx.x + i * (int)gridDim.x) * TR_ROWS;
+    const int row0 = ((int)blockIdx.x + i * (int)gridDim.x) * ROWS;
     const uint32_t bar = smem_u32(&full[s]);
     uint32_t dst = smem_u32(base + s * C::STAGE_BYTES);
     mbar_expect_tx(&full[s], C::STAGE_BYTES);
-    tma_load_2d(dst, pm0, 0, row0, bar);
-    dst += C::XSUB_BYTES;
-    if constexpr (NSUB == 2) {
-      tma_load_2d(dst, pm1, colx1, row0, bar);
-      dst += C::XSUB_BYTES;
-    }
+#pragma unroll
+    for (int q = 0; q < NS0; ++q) tma_load_2d(dst + q * C::XSUB_BYTES, pm0, q * WS, row0, bar);
+#pragma unroll
+    for (int q = 0; q < NS1; ++q) tma_load_2d(dst + (NS0 + q) * C::XSUB_BYTES, pm1, q * WS, row0, bar);
+    dst += C::NSUB * C::XSUB_BYTES;
 #pragma unroll
     for (int ms = 0; ms < C::MSUB; ++ms) tma_load_2d(dst + ms * C::GSUB_BYTES, pmg, ms * C::GWS, row0, bar);
   };
   if (tid == 0)
     for (int i = 0; i < C::STAGES && i < my_tiles; ++i) issue(i);
 
-  float acc[4][4];  // acc[m][k]
+  float acc[C::KPT][4][4];  // acc[j][m][k]
   float bs[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-  for (int a = 0; a < 4; ++a)
+  for (int j = 0; j < C::KPT; ++j)
 #pragma unroll
-    for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
-  // which sub-tile / chunk of a row this thread reads (fixed for the whole kernel)
-  const int xsub = (kb * 4) / WS, xchunk = ((kb * 4) % WS) / 4;
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) acc[j][a][b] = 0.f;
+  // which box / 16-byte chunk of a row this thread reads (fixed for the whole kernel)
+  const int k0 = kg * 4 * C::KPT;  // first gw column of the thread
+  const int xsub = k0 / WS, xchunk = (k0 % WS) / 4;
   const int gsub = (mb * 4) / C::GWS, gchunk = ((mb * 4) % C::GWS) / 4;
 
   for (int i = 0; i < my_tiles; ++i) {
     const int s = i % C::STAGES;
     mbar_wait(&full[s], (uint32_t)(i / C::STAGES) & 1u);
     const uint8_t* X = base + s * C::STAGE_BYTES + xsub * C::XSUB_BYTES;
-    const uint8_t* G = base + s * C::STAGE_BYTES + NSUB * C::XSUB_BYTES + gsub * C::GSUB_BYTES;
+    const uint8_t* G = base + s * C::STAGE_BYTES + C::NSUB * C::XSUB_BYTES + gsub * C::GSUB_BYTES;
     // rows past n are zero-filled by the TMA unit: they add nothing
 #pragma unroll 8
     for (int rr = 0; rr < C::RPT; ++rr) {
       const int row = rq * C::RPT + rr;
-      const float4 x = *reinterpret_cast<const float4*>(X + sw_off<WS>(row, xchunk));
       const float4 g = *reinterpret_cast<const float4*>(G + sw_off<C::GWS>(row, gchunk));
-      ffma2_bc(g.x, x.x, x.y, acc[0][0], acc[0][1]), ffma2_bc(g.x, x.z, x.w, acc[0][2], acc[0][3]);
-      ffma2_bc(g.y, x.x, x.y, acc[1][0], acc[1][1]), ffma2_bc(g.y, x.z, x.w, acc[1][2], acc[1][3]);
-      ffma2_bc(g.z, x.x, x.y, acc[2][0], acc[2][1]), ffma2_bc(g.z, x.z, x.w, acc[2][2], acc[2][3]);
-      ffma2_bc(g.w, x.x, x.y, acc[3][0], acc[3][1]), ffma2_bc(g.w, x.z, x.w, acc[3][2], acc[3][3]);
-      if (kb == 0) bs[0] += g.x, bs[1] += g.y, bs[2] += g.z, bs[3] += g.w;
+#pragma unroll
+      for (int j = 0; j < C::KPT; ++j) {
+        const float4 x = *reinterpret_cast<const float4*>(X + sw_off<WS>(row, xchunk + j));
+        ffma2_bc(g.x, x.x, x.y, acc[j][0][0], acc[j][0][1]), ffma2_bc(g.x, x.z, x.w, acc[j][0][2], acc[j][0][3]);
+        ffma2_bc(g.y, x.x, x.y, acc[j][1][0], acc[j][1][1]), ffma2_bc(g.y, x.z, x.w, acc[j][1][2], acc[j][1][3]);
+        ffma2_bc(g.z, x.x, x.y, acc[j][2][0], acc[j][2][1]), ffma2_bc(g.z, x.z, x.w, acc[j][2][2], acc[j][2][3]);
+        ffma2_bc(g.w, x.x, x.y, acc[j][3][0], acc[j][3][1]), ffma2_bc(g.w, x.z, x.w, acc[j][3][2], acc[j][3][3]);
+      }
+      if (kg == 0) bs[0] += g.x, bs[1] += g.y, bs[2] += g.z, bs[3] += g.w;
     }
     __syncthreads();
     if (tid == 0 && i + C::STAGES < my_tiles) issue(i + C::STAGES);
@@ -329,10 +345,17 @@ tma_rows_tn_kernel(const __grid_constant__ CUtensorMap mapx0, const __grid_const
 
   // CTA reduction over the row slices in shared memory, then one set of global reductions per CTA
 #pragma unroll
-  for (int a = 0; a < 4; ++a)
+  for (int j = 0; j < C::KPT; ++j)
 #pragma unroll
-    for (int b = 0; b < 4; ++b) atomicAdd(&R[(mb * 4 + a) * C::KP + kb * 4 + b], acc[a][b]);
-  if (kb == 0) {
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        if constexpr (C::RQ > 1)
+          atomicAdd(&R[(mb * 4 + a) * C::KP + k0 + 4 * j + b], acc[j][a][b]);
+        else
+          R[(mb * 4 + a) * C::KP + k0 + 4 * j + b] = acc[j][a][b];  // one writer per element
+      }
+  if (kg == 0) {
 #pragma unroll
     for (int a = 0; a < 4; ++a) atomicAdd(&R[MP * C::KP + mb * 4 + a], bs[a]);
   }
@@ -403,12 +426,14 @@ int nn_go(const float* a1, int64_t ld1, int c1, const float* a2, int64_t ld2, in
   return B200_OK;
 }
 
-template <int WS, int NSUB, int MP>
-int tn_go(const float* gy, const float* a1, int64_t ld1, int c1, const float* a2, int64_t ld2, int c2, float* gw, float* gb,
+// one TN launch: X = NS0 boxes of a1 (+ NS1 boxes of a2), gw columns [0, WS (NS0 + NS1)) of a row-major matrix with leading
+// dimension gw_ld (the caller offsets gw when the weight's columns are covered by two launches)
+template <int WS, int NS0, int NS1, int MP, int ROWS>
+int tn_go(const float* gy, const float* a1, int64_t ld1, const float* a2, int64_t ld2, float* gw, int gw_ld, float* gb,
           int64_t n, cudaStream_t st) {
-  using C = TnCfg<WS, NSUB, MP>;
-  auto kern = tma_rows_tn_kernel<WS, NSUB, MP>;
-  const int ntiles = (int)ceil_div(n, TR_ROWS);
+  using C = TnCfg<WS, NS0, NS1, MP, ROWS>;
+  auto kern = tma_rows_tn_kernel<WS, NS0, NS1, MP, ROWS>;
+  const int ntiles = (int)ceil_div(n, ROWS);
   static thread_local int occ = -1;
   if (occ < 0) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
@@ -420,28 +445,22 @@ int tn_go(const float* gy, const float* a1, int64_t ld1, int c1, const float* a2
   const int64_t cap = (int64_t)num_sms() * occ;
   const int grid = (int)(ntiles < cap ? ntiles : cap);
   CUtensorMap m0, m1, mg;
-  if (!make_map(&m0, a1, ld1, c1, n, WS) || !make_map(&mg, gy, MP, MP, n, C::GWS)) {
+  if (!make_map(&m0, a1, ld1, WS * NS0, n, WS, ROWS) || !make_map(&mg, gy, MP, MP, n, C::GWS, ROWS)) {
     set_error("tma_rows: cuTensorMapEncodeTiled failed (weight gradient)");
     return B200_E_CUDA;
   }
-  int col1 = 0;
   m1 = m0;
-  if (NSUB == 2) {
-    if (c2 > 0) {
-      if (!make_map(&m1, a2, ld2, c2, n, WS)) {
-        set_error("tma_rows: cuTensorMapEncodeTiled failed (second segment)");
-        return B200_E_CUDA;
-      }
-    } else {
-      col1 = WS;
-    }
+  if (NS1 > 0 && !make_map(&m1, a2, ld2, WS * NS1, n, WS, ROWS)) {
+    set_error("tma_rows: cuTensorMapEncodeTiled failed (second segment)");
+    return B200_E_CUDA;
   }
-  kern<<<grid, TR_THREADS, C::SMEM, st>>>(m0, m1, col1, mg, gw, c1 + c2, gb, ntiles);
+  kern<<<grid, TR_THREADS, C::SMEM, st>>>(m0, m1, mg, gw, gw_ld, gb, ntiles);
   B200_CHECK_LAUNCH("tma_rows_tn_kernel");
   return B200_OK;
 }
 
 bool m_ok(int m) { return m == 16 || m == 32 || m == 64; }
+bool seg_ok(const float* a, int64_t ld, int c) { return a && al16(a) && ld % 4 == 0 && ld >= c; }
 
 }  // namespace
 
@@ -480,21 +499,55 @@ int launch_tma_rows_nn(const float* a1, int64_t ld1, int c1, const float* a2, in
   return B200_E_UNSUPPORTED;
 }
 
+// weight gradient: cout in {16, 32, 64, 128}; rows = one segment of 16 / 32 / 64 / 128 columns, or 32 + 32, or 128 + 32 (the
+// decoder's concatenated inputs).  32 x 128, 64 x 128 and 128(+32) x 32 use 64-row boxes.
+static int tn_plan(int c1, int c2, int cout) {  // 0 = unsupported
+  if (c2 == 0) {
+    if ((c1 == 16 || c1 == 32 || c1 == 64) && (cout == 16 || cout == 32 || cout == 64)) return 1;
+    if ((c1 == 32 || c1 == 64) && cout == 128) return 2;
+    if (c1 == 128 && cout == 32) return 3;
+    return 0;
+  }
+  if (c1 == 32 && c2 == 32 && (cout == 16 || cout == 32 || cout == 64)) return 1;
+  if (c1 == 128 && c2 == 32 && cout == 32) return 4;
+  return 0;
+}
+
 bool tma_rows_tn_ok(int64_t n, const float* gy, int cout, const float* a1, int64_t ld1, int c1, const float* a2, int64_t ld2,
                     int c2) {
-  if (n < 8192 || n > (int64_t)1 << 30 || !m_ok(cout) || !gy || !al16(gy) || !encode_fn()) return false;
-  return k_side(a1, ld1, c1, a2, ld2, c2).ok;
+  if (n < 8192 || n > (int64_t)1 << 30 || !gy || !al16(gy) || !encode_fn()) return false;
+  if (!seg_ok(a1, ld1, c1) || (c2 > 0 && !seg_ok(a2, ld2, c2))) return false;
+  return tn_plan(c1, c2, cout) != 0;
 }
 
 int launch_tma_rows_tn(const float* gy, int cout, const float* a1, int64_t ld1, int c1, const float* a2, int64_t ld2, int c2,
                        float* gw, float* gb, int64_t n, cudaStream_t st) {
-  const KSide k = k_side(a1, ld1, c1, a2, ld2, c2);
-#define B200_TN(WS_, NS_, MP_) \
-  if (k.ws == WS_ && k.nsub == NS_ && cout == MP_) return tn_go<WS_, NS_, MP_>(gy, a1, ld1, c1, a2, ld2, c2, gw, gb, n, st);
-  B200_TN(16, 1, 16) B200_TN(16, 1, 32) B200_TN(16, 1, 64)
-  B200_TN(32, 1, 16) B200_TN(32, 1, 32) B200_TN(32, 1, 64)
-  B200_TN(32, 2, 16) B200_TN(32, 2, 32) B200_TN(32, 2, 64)
+  const int ktot = c1 + c2;
+  switch (tn_plan(c1, c2, cout)) {
+    case 1: {
+      const int ws = (c1 == 16) ? 16 : 32, ns0 = c1 / ws, ns1 = c2 / ws;
+#define B200_TN(WS_, N0_, N1_, MP_) \
+  if (ws == WS_ && ns0 == N0_ && ns1 == N1_ && cout == MP_) return tn_go<WS_, N0_, N1_, MP_, TR_ROWS>(gy, a1, ld1, a2, ld2, gw, ktot, gb, n, st);
+      B200_TN(16, 1, 0, 16) B200_TN(16, 1, 0, 32) B200_TN(16, 1, 0, 64)
+      B200_TN(32, 1, 0, 16) B200_TN(32, 1, 0, 32) B200_TN(32, 1, 0, 64)
+      B200_TN(32, 2, 0, 16) B200_TN(32, 2, 0, 32) B200_TN(32, 2, 0, 64)
+      B200_TN(32, 1, 1, 16) B200_TN(32, 1, 1, 32) B200_TN(32, 1, 1, 64)
 #undef B200_TN
+      break;
+    }
+    case 2:
+      if (c1 == 32) return tn_go<32, 1, 0, 128, 64>(gy, a1, ld1, nullptr, 0, gw, ktot, gb, n, st);
+      return tn_go<32, 2, 0, 128, 64>(gy, a1, ld1, nullptr, 0, gw, ktot, gb, n, st);
+    case 3:
+      return tn_go<32, 4, 0, 32, 64>(gy, a1, ld1, nullptr, 0, gw, ktot, gb, n, st);
+    case 4: {  // [a1 (128) | a2 (32)]: two launches over disjoint column ranges of gw, the bias gradient rides with the first
+      const int rc = tn_go<32, 4, 0, 32, 64>(gy, a1, ld1, nullptr, 0, gw, ktot, gb, n, st);
+      if (rc != B200_OK) return rc;
+      return tn_go<32, 1, 0, 32, TR_ROWS>(gy, a2, ld2, nullptr, 0, gw + c1, ktot, nullptr, n, st);
+    }
+    default:
+      break;
+  }
   set_error("tma_rows: unsupported shape");
   return B200_E_UNSUPPORTED;
 }

@@ -9,7 +9,8 @@ from myria3d_b200.ops import _p, _stream
 lib = _lib.load()
 lib.b200_set_option(b"tma_rows", 7)
 dev = "cuda"
-for n, c1, c2, cout in [(8192, 32, 0, 32), (8192, 16, 0, 16), (8192, 64, 0, 64), (8192, 32, 32, 32), (8300, 32, 0, 16), (8192, 16, 0, 64)]:
+for n, c1, c2, cout in [(8192, 32, 0, 32), (8192, 16, 0, 16), (8192, 64, 0, 64), (8192, 32, 32, 32), (8300, 32, 0, 16), (8192, 16, 0, 64),
+                        (8192, 32, 0, 128), (8200, 64, 0, 128), (8192, 128, 32, 32), (8300, 128, 0, 32)]:  # the last four: weight gradient only
     k = c1 + c2
     r = torch.arange(n, device=dev, dtype=torch.float32)[:, None]
     x = r * 128 + torch.arange(k, device=dev, dtype=torch.float32)[None, :]  # exact in fp32

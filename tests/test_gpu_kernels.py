@@ -371,7 +371,8 @@ def test_linear_row_streaming_kernel(lib, n, c1, c2, cout):
 
 @pytest.mark.parametrize("n,c1,c2,cout", [(204800, 32, 0, 32), (51200, 16, 0, 32), (8269, 32, 32, 32), (30000, 64, 0, 32),
                                           (20000, 32, 0, 64), (9000, 16, 0, 16), (12345, 64, 0, 64), (10000, 32, 0, 16),
-                                          (8200, 16, 0, 64), (40001, 64, 0, 16), (204800, 32, 32, 32)])
+                                          (8200, 16, 0, 64), (40001, 64, 0, 16), (204800, 32, 32, 32),
+                                          (51200, 32, 0, 128), (20001, 64, 0, 128), (51200, 128, 32, 32), (12800, 128, 0, 32)])
 def test_linear_tma_rows(lib, n, c1, c2, cout):
     """tma_rows.cu (2-D tensor-map TMA boxes through an mbarrier ring, persistent CTAs; 16/32/64-channel layers on
     >= 8192 rows): forward + fp64 BatchNorm column statistics (|mean| >> std), input gradients of both segments, weight
@@ -406,18 +407,20 @@ def test_linear_tma_rows(lib, n, c1, c2, cout):
         y0, stats0, ag0 = run()
     finally:
         lib.b200_set_option(b"tma_rows", before)
-    assert_close(y, y_ref, atol=2e-5, rtol=1e-5 if c1 + c2 == 64 and cout == 64 else 2e-6, what="tma_rows y")
+    wide = (c1 + c2 == 64 and cout == 64) or c1 + c2 > 64 or cout > 64
+    assert_close(y, y_ref, atol=3e-5 if wide else 2e-5, rtol=1e-5 if wide else 2e-6, what="tma_rows y")
     st = stats.sum(0)
     ycpu = y.double().cpu()
     mean = st[:cout] / n
     var = st[cout:] / n - mean * mean
-    # (64 x 64 forward / input gradient stay on tc_nt.cu / the 64 x 64-tile FMA kernel: statistics of the tcgen05 epilogue)
-    wide = c1 + c2 == 64 and cout == 64
+    # (64 x 64 and the >= 128-wide shapes: forward / input gradient stay on tc_nt.cu / the tile FMA kernels -- statistics of
+    # the tcgen05 epilogue, 3xTF32 products; their weight gradients still go through tma_rows_tn)
+    wide = (c1 + c2 == 64 and cout == 64) or c1 + c2 > 64 or cout > 64
     assert_close(mean, ycpu.mean(0), atol=0.0, rtol=1e-7 if wide else 1e-9, what="column means")
     assert_close(var, ycpu.var(0, unbiased=False), atol=0.0, rtol=1e-4 if wide else 1e-6, what="column variances")
     assert rel_err(ag[0].grad, ga_ref[:, :c1]) < (1e-5 if wide else 2e-6), rel_err(ag[0].grad, ga_ref[:, :c1])
     if c2:
-        assert rel_err(ag[3].grad, ga_ref[:, c1:]) < 2e-6, rel_err(ag[3].grad, ga_ref[:, c1:])
+        assert rel_err(ag[3].grad, ga_ref[:, c1:]) < (1e-5 if wide else 2e-6), rel_err(ag[3].grad, ga_ref[:, c1:])
     assert rel_err(ag[1].grad, gw_ref) < 5e-6, rel_err(ag[1].grad, gw_ref)  # fp32 accumulation over n rows
     assert rel_err(ag[2].grad, gb_ref) < 5e-6, rel_err(ag[2].grad, gb_ref)
     # the kernels they stand in for agree to fp32 round-off (different summation orders)
