@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define B200_ABI_VERSION 4
+#define B200_ABI_VERSION 5
 
 #define B200_OK 0
 #define B200_E_INVALID 1     /* bad argument (null pointer, unsupported size/alignment) */
@@ -51,6 +51,9 @@ int b200_check_device(void);
  *   "tma_rows"      bitmask of the Linear kernels of the 16/32/64-channel layers on >= 8192 rows that run as TMA-fed
  *                   persistent row-streaming kernels (tma_rows.cu; 2-D tensor maps, mbarrier ring): 1 forward,
  *                   2 input gradient, 4 weight gradient (default 7); cleared bits select the register-staged kernels.
+ *   "bn_backward_fused"  0 (default) / 1: b200_affine_act_bwd runs reduce + apply of the small levels as ONE launch with a
+ *                   grid barrier (measured on a B200: 16.8 us against 8.0 + 5.5 us for the two kernels -- a grid of
+ *                   #SMs / 2 CTAs is too small for either phase -- so it is off; kept as an A/B switch).
  *   "knn_points_per_cell"  average occupancy of the bucket grid of b200_knn_grid; 0 (default) = automatic
  *                   (6 for k < 8, 8 for k < 24, 16 above); results do not depend on it (exact search).
  *   "tc_timeline"   device pointer (as integer) to 128 int64 receiving clock64() marks of CTA 0 of the tcgen05 GEMMs
@@ -261,6 +264,18 @@ int b200_affine_act_bwd_apply(const float* grad_out, const float* out, float slo
                               const double* red2, const float* scale2, float* grad_y2,
                               float* grad_gamma2, float* grad_beta2,
                               int64_t n, int32_t c, void* stream);
+/* Train-mode backward of the same block in ONE call: b200_affine_act_bwd_reduce followed by b200_affine_act_bwd_apply
+ * (autograd of BatchNorm1d + LeakyReLU inside SharedMLP, pyg_randla_net.py:97-109, and of the block tail :186-187).
+ * red1 / red2 (fp64 [2c] each) and `barrier` (one uint32) must be ZERO on entry; they are scratch.  When n * c <= 2^21,
+ * c % 4 == 0, the rows are 16-byte aligned and option "bn_backward_fused" is 1 (default 0), both passes run as one kernel with a
+ * grid barrier in between (at most #SMs / 2 CTAs, two fit an SM: always co-resident); otherwise, or with
+ * barrier == NULL, as the two launches.  Results are those of the two-call sequence. */
+int b200_affine_act_bwd(const float* grad_out, const float* out, float slope,
+                        const float* y1, const float* gamma1, const float* mean1, const float* invstd1, double* red1,
+                        float* grad_y1, float* grad_gamma1, float* grad_beta1,
+                        const float* y2, const float* gamma2, const float* mean2, const float* invstd2, double* red2,
+                        float* grad_y2, float* grad_gamma2, float* grad_beta2,
+                        uint32_t* barrier, int64_t n, int32_t c, void* stream);
 
 /* ------------------------------------------------------- loss --------------------------
  * torch.nn.CrossEntropyLoss(weight | NULL, ignore_index, label_smoothing=0, reduction="mean") on [n, c] logits and

@@ -60,13 +60,15 @@ _SIGNATURES = {
     "b200_cross_entropy_bwd": (c_int, [_P, _P, _P, c_int64, c_int32, c_int64, _P, _P, _P, _P]),
     "b200_affine_act_fwd": (c_int, [_P, _P, _P, _P, _P, _P, c_float, _P, c_int64, c_int32, _P]),
     "b200_affine_act_bwd_reduce": (c_int, [_P, _P, c_float, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int32, _P]),
+    "b200_affine_act_bwd": (c_int, [_P, _P, c_float, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64,
+                                    c_int32, _P]),
     "b200_affine_act_bwd_apply": (
         c_int,
         [_P, _P, c_float, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int32, _P],
     ),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 _lib = None
 

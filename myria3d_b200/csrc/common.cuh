@@ -85,6 +85,7 @@ int launch_tma_rows_tn(const float* gy, int cout, const float* a1, int64_t ld1, 
                        float* gw, float* gb, int64_t n, cudaStream_t st);
 void set_grid_points_per_cell(int v);  // knn_grid.cu (tuning knob, b200_set_option("knn_points_per_cell"))
 int get_grid_points_per_cell();
+bool bn_backward_fused_enabled();  // runtime.cu: b200_set_option("bn_backward_fused", 0/1)
 bool tc_path_enabled(int bit);  // runtime.cu: b200_set_option("tensor_core_paths", mask) -- per-kernel-family A/B switch
 bool tensor_cores_enabled();  // runtime.cu: b200_set_option("tensor_cores", 0) selects the FMA kernels (A/B switch)
 

@@ -689,14 +689,13 @@ affine_act_bwd_reduce_kernel(const float* __restrict__ go, const float* __restri
 
 // float4 version (c % 4 == 0): a thread owns 4 channels of every (rows-per-pass)-th row -- 4x fewer load instructions
 // and 4x more bytes in flight per thread than the scalar kernel; the CTA covers c/4 lanes x 256/(c/4) rows per pass.
-__global__ void __launch_bounds__(RED_THREADS)
-affine_act_bwd_reduce_vec4_kernel(const float* __restrict__ go, const float* __restrict__ out, float slope,
-                                  const float* __restrict__ y1, const float* __restrict__ mean1,
-                                  const float* __restrict__ invstd1, double* __restrict__ red1,
-                                  const float* __restrict__ y2, const float* __restrict__ mean2,
-                                  const float* __restrict__ invstd2, double* __restrict__ red2, int64_t n, int c,
-                                  int lanes /* pow2 >= min(c/4, 256) */) {
-  __shared__ float part[12][RED_THREADS];
+__device__ __forceinline__ void
+bwd_reduce_vec4_body(const float* __restrict__ go, const float* __restrict__ out, float slope,
+                     const float* __restrict__ y1, const float* __restrict__ mean1,
+                     const float* __restrict__ invstd1, double* __restrict__ red1,
+                     const float* __restrict__ y2, const float* __restrict__ mean2,
+                     const float* __restrict__ invstd2, double* __restrict__ red2, int64_t n, int c,
+                     int lanes /* pow2 >= min(c/4, 256) */, int bid, int nblk, float (*part)[RED_THREADS]) {
   const int tid = threadIdx.x;
   const int lane = tid % lanes, rsub = tid / lanes, rstep = RED_THREADS / lanes;
   const int c4 = c >> 2;
@@ -709,7 +708,7 @@ affine_act_bwd_reduce_vec4_kernel(const float* __restrict__ go, const float* __r
       if (y2) m2 = __ldg(reinterpret_cast<const float4*>(mean2) + q), is2 = __ldg(reinterpret_cast<const float4*>(invstd2) + q);
       const float m1a[4] = {m1.x, m1.y, m1.z, m1.w}, i1a[4] = {is1.x, is1.y, is1.z, is1.w};
       const float m2a[4] = {m2.x, m2.y, m2.z, m2.w}, i2a[4] = {is2.x, is2.y, is2.z, is2.w};
-      for (int64_t i = (int64_t)blockIdx.x * rstep + rsub; i < n; i += (int64_t)gridDim.x * rstep) {
+      for (int64_t i = (int64_t)bid * rstep + rsub; i < n; i += (int64_t)nblk * rstep) {
         const int64_t off = i * c4 + q;
         const float4 g4 = __ldg(reinterpret_cast<const float4*>(go) + off);
         const float4 a4 = __ldg(reinterpret_cast<const float4*>(y1) + off);
@@ -762,6 +761,17 @@ affine_act_bwd_reduce_vec4_kernel(const float* __restrict__ go, const float* __r
   }
 }
 
+__global__ void __launch_bounds__(RED_THREADS)
+affine_act_bwd_reduce_vec4_kernel(const float* __restrict__ go, const float* __restrict__ out, float slope,
+                                  const float* __restrict__ y1, const float* __restrict__ mean1,
+                                  const float* __restrict__ invstd1, double* __restrict__ red1,
+                                  const float* __restrict__ y2, const float* __restrict__ mean2,
+                                  const float* __restrict__ invstd2, double* __restrict__ red2, int64_t n, int c, int lanes) {
+  __shared__ float part[12][RED_THREADS];
+  bwd_reduce_vec4_body(go, out, slope, y1, mean1, invstd1, red1, y2, mean2, invstd2, red2, n, c, lanes, (int)blockIdx.x,
+                       (int)gridDim.x, part);
+}
+
 struct BnBranch {
   const float* y;
   const float* gamma;
@@ -775,29 +785,29 @@ struct BnBranch {
 };
 
 template <int V>
-__global__ void __launch_bounds__(256)
-affine_act_bwd_apply_kernel(const float* __restrict__ go, const float* __restrict__ out, float slope, BnBranch b1,
-                            BnBranch b2, int64_t n, int c) {
+__device__ __forceinline__ void
+bwd_apply_body(const float* __restrict__ go, const float* __restrict__ out, float slope, const BnBranch& b1,
+               const BnBranch& b2, int64_t n, int c, int bid, int nblk, float* __restrict__ coef) {
   const int64_t total = n * c;
   const double inv_n = 1.0 / (double)n;
   // parameter gradients (train-mode BatchNorm): accumulated once, by the first CTA, into the caller's buffers
   // (the parameters' .grad, or zero-filled temporaries)
-  if (blockIdx.x == 0) {
+  if (bid == 0) {
     for (int ch = threadIdx.x; ch < c; ch += 256) {
       if (b1.red && b1.grad_gamma) {
-        b1.grad_gamma[ch] += (float)b1.red[c + ch];
-        b1.grad_beta[ch] += (float)b1.red[ch];
+        b1.grad_gamma[ch] += (float)__ldcg(b1.red + c + ch);
+        b1.grad_beta[ch] += (float)__ldcg(b1.red + ch);
       }
       if (b2.y && b2.red && b2.grad_gamma) {
-        b2.grad_gamma[ch] += (float)b2.red[c + ch];
-        b2.grad_beta[ch] += (float)b2.red[ch];
+        b2.grad_gamma[ch] += (float)__ldcg(b2.red + c + ch);
+        b2.grad_beta[ch] += (float)__ldcg(b2.red + ch);
       }
     }
   }
   // grad_y = k1 * (g - mg) - k4 * (y - mean) per channel, with k1 = gamma * invstd, mg = red[0]/n, k4 = k1 * invstd *
   // red[1]/n (train) or k1 = scale, mg = k4 = 0 (eval / plain affine): the four coefficients of both branches are
   // staged once per CTA (the element loop used 3 global + 2 fp64 loads and 2 fp64 multiplies per ELEMENT)
-  extern __shared__ __align__(16) float coef[];  // [branch][k1 | mg | k4 | mean][c]
+  // coef (shared memory of the caller): [branch][k1 | mg | k4 | mean][c]
   for (int ch = threadIdx.x; ch < c; ch += 256) {
 #pragma unroll
     for (int br = 0; br < 2; ++br) {
@@ -807,8 +817,8 @@ affine_act_bwd_apply_kernel(const float* __restrict__ go, const float* __restric
         if (bb.red) {
           const float is = __ldg(bb.invstd + ch);
           k1 = __ldg(bb.gamma + ch) * is;
-          mg = (float)(bb.red[ch] * inv_n);
-          k4 = k1 * is * (float)(bb.red[c + ch] * inv_n);
+          mg = (float)(__ldcg(bb.red + ch) * inv_n);
+          k4 = k1 * is * (float)(__ldcg(bb.red + c + ch) * inv_n);
           mean = __ldg(bb.mean + ch);
         } else {
           k1 = __ldg(bb.scale + ch);
@@ -820,7 +830,7 @@ affine_act_bwd_apply_kernel(const float* __restrict__ go, const float* __restric
   }
   __syncthreads();
   const bool need_y1 = b1.red != nullptr, need_y2 = b2.y && b2.red;
-  for (int64_t idx = ((int64_t)blockIdx.x * 256 + threadIdx.x) * V; idx < total; idx += (int64_t)gridDim.x * 256 * V) {
+  for (int64_t idx = ((int64_t)bid * 256 + threadIdx.x) * V; idx < total; idx += (int64_t)nblk * 256 * V) {
     const int ch0 = (int)(idx % c);
     float g[V], o[V], y1v[V], y2v[V];
 #pragma unroll
@@ -877,6 +887,45 @@ affine_act_bwd_apply_kernel(const float* __restrict__ go, const float* __restric
       if (b2.y) b2.grad_y[idx] = r2[0];
     }
   }
+}
+
+template <int V>
+__global__ void __launch_bounds__(256)
+affine_act_bwd_apply_kernel(const float* __restrict__ go, const float* __restrict__ out, float slope, BnBranch b1,
+                            BnBranch b2, int64_t n, int c) {
+  extern __shared__ __align__(16) float coef_smem[];
+  bwd_apply_body<V>(go, out, slope, b1, b2, n, c, (int)blockIdx.x, (int)gridDim.x, coef_smem);
+}
+
+// Reduce + apply of a train-mode BatchNorm backward in ONE launch (small levels: two latency-bound kernels and the gap
+// between them cost more than the bytes).  MEASURED SLOWER (round 2: 15 launches x 16.8 us against 15 x (8.0 + 5.5) us of
+// the two kernels; the co-residency rule below caps the grid at #SMs / 2 CTAs, too few for either phase), so the option
+// "bn_backward_fused" is off by default and the two-kernel path runs; kept as an A/B switch and as a tested example of a
+// safe software grid barrier.  The grid is at most half the SMs, two CTAs of this kernel fit an SM, and no
+// other kernel of the library spins on a condition: all CTAs become co-resident, so the software grid barrier between
+// the two phases (a counter the caller zeroed; acquire spin, bounded: a violated assumption traps instead of hanging)
+// is safe.  The sums travel through the same fp64 `red` buffers as in the two-kernel path.
+__global__ void __launch_bounds__(256, 2)
+affine_act_bwd_fused_kernel(const float* __restrict__ go, const float* __restrict__ out, float slope, BnBranch b1, BnBranch b2,
+                            double* __restrict__ red1, double* __restrict__ red2, unsigned int* __restrict__ barrier,
+                            int64_t n, int c, int lanes) {
+  __shared__ float part[12][RED_THREADS];
+  extern __shared__ __align__(16) float coef_smem[];
+  bwd_reduce_vec4_body(go, out, slope, b1.y, b1.mean, b1.invstd, red1, b2.y, b2.mean, b2.invstd, red2, n, c, lanes,
+                       (int)blockIdx.x, (int)gridDim.x, part);
+  __threadfence();  // this CTA's atomics are performed before its arrival is visible
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    atomicAdd(barrier, 1u);
+    unsigned int seen = 0;
+    for (unsigned int spin = 0; spin < (1u << 22); ++spin) {  // ~ seconds; the real wait is microseconds
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(barrier) : "memory");
+      if (seen >= gridDim.x) break;
+    }
+    if (seen < gridDim.x) __trap();
+  }
+  __syncthreads();
+  bwd_apply_body<4>(go, out, slope, b1, b2, n, c, (int)blockIdx.x, (int)gridDim.x, coef_smem);
 }
 
 static int elementwise_grid(int64_t work_items) {
@@ -1110,4 +1159,38 @@ extern "C" int b200_affine_act_bwd_apply(const float* grad_out, const float* out
     affine_act_bwd_apply_kernel<1><<<elementwise_grid(total), 256, 8 * c * sizeof(float), st>>>(grad_out, out, slope, b1, b2, n, c);
   B200_CHECK_LAUNCH("affine_act_bwd_apply_kernel");
   return B200_OK;
+}
+
+extern "C" int b200_affine_act_bwd(const float* grad_out, const float* out, float slope, const float* y1, const float* gamma1,
+                                   const float* mean1, const float* invstd1, double* red1, float* grad_y1, float* grad_gamma1,
+                                   float* grad_beta1, const float* y2, const float* gamma2, const float* mean2,
+                                   const float* invstd2, double* red2, float* grad_y2, float* grad_gamma2, float* grad_beta2,
+                                   uint32_t* barrier, int64_t n, int32_t c, void* stream) {
+  B200_REQUIRE(grad_out && y1 && gamma1 && mean1 && invstd1 && red1 && grad_y1 && c > 0, B200_E_INVALID,
+               "b200_affine_act_bwd: null pointer (train-mode BatchNorm backward: statistics and `red` are required)");
+  B200_REQUIRE(slope == 1.f || out, B200_E_INVALID, "b200_affine_act_bwd: activation needs `out`");
+  B200_REQUIRE(!y2 || (gamma2 && mean2 && invstd2 && red2 && grad_y2), B200_E_INVALID, "b200_affine_act_bwd: second branch incomplete");
+  if (n <= 0) return B200_OK;
+  const bool vec = c % 4 == 0 && c <= 1024 && aligned16(grad_out) && aligned16(y1) && aligned16(grad_y1) &&
+                   (slope == 1.f || aligned16(out)) && aligned16(mean1) && aligned16(invstd1) &&
+                   (!y2 || (aligned16(y2) && aligned16(grad_y2) && aligned16(mean2) && aligned16(invstd2)));
+  if (vec && barrier && bn_backward_fused_enabled() && n * (int64_t)c <= ((int64_t)1 << 21)) {
+    int lanes = 1;
+    while (lanes < c / 4 && lanes < RED_THREADS) lanes <<= 1;
+    const int rstep = RED_THREADS / lanes;
+    int64_t blocks = ceil_div(n, (int64_t)rstep * 4);
+    const int64_t cap = num_sms() / 2 > 0 ? num_sms() / 2 : 1;  // two instances can always be co-resident
+    if (blocks > cap) blocks = cap;
+    BnBranch b1{y1, gamma1, mean1, invstd1, red1, nullptr, grad_y1, grad_gamma1, grad_beta1};
+    BnBranch b2{y2, gamma2, mean2, invstd2, red2, nullptr, grad_y2, grad_gamma2, grad_beta2};
+    affine_act_bwd_fused_kernel<<<(unsigned)blocks, RED_THREADS, 8 * c * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+        grad_out, out, slope, b1, b2, red1, red2, barrier, n, c, lanes);
+    B200_CHECK_LAUNCH("affine_act_bwd_fused_kernel");
+    return B200_OK;
+  }
+  const int rc = b200_affine_act_bwd_reduce(grad_out, out, slope, y1, mean1, invstd1, red1, y2, mean2, invstd2, red2, n, c, stream);
+  if (rc != B200_OK) return rc;
+  return b200_affine_act_bwd_apply(grad_out, out, slope, y1, gamma1, mean1, invstd1, red1, nullptr, grad_y1, grad_gamma1,
+                                   grad_beta1, y2, gamma2, mean2, invstd2, red2, nullptr, grad_y2, grad_gamma2, grad_beta2, n, c,
+                                   stream);
 }

@@ -28,7 +28,9 @@ void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 static std::atomic<int> g_tensor_cores{1};
 static std::atomic<int> g_tc_paths{0x1f};  // bit 0 linear forward, 1 linear input gradient, 2 wide weight gradient, 3 narrow weight gradient, 4 LFA
 static std::atomic<int> g_tma_rows{7};  // bit 0 linear forward, 1 linear input gradient, 2 weight gradient (tma_rows.cu)
+static std::atomic<int> g_bn_fused{0};   // one-launch BatchNorm backward for the small levels (pointwise.cu): measured slower, off
 static std::atomic<long long*> g_tc_timeline{nullptr};
+bool bn_backward_fused_enabled() { return g_bn_fused.load(std::memory_order_relaxed) != 0; }
 bool tma_rows_enabled(int bit) { return (g_tma_rows.load(std::memory_order_relaxed) & bit) != 0; }
 bool tensor_cores_enabled() { return g_tensor_cores.load(std::memory_order_relaxed) != 0; }
 bool tc_path_enabled(int bit) {
@@ -77,11 +79,15 @@ int b200_set_option(const char* key, int64_t value) {
     b200::g_tma_rows.store((int)value, std::memory_order_relaxed);
     return B200_OK;
   }
+  if (strcmp(key, "bn_backward_fused") == 0) {
+    b200::g_bn_fused.store(value != 0, std::memory_order_relaxed);
+    return B200_OK;
+  }
   if (strcmp(key, "tc_timeline") == 0) {
     b200::g_tc_timeline.store(reinterpret_cast<long long*>(static_cast<intptr_t>(value)), std::memory_order_relaxed);
     return B200_OK;
   }
-  b200::set_error("b200_set_option: unknown option '%s' (known: tensor_cores, tensor_core_paths, tma_rows, knn_points_per_cell, tc_timeline)", key);
+  b200::set_error("b200_set_option: unknown option '%s' (known: tensor_cores, tensor_core_paths, tma_rows, bn_backward_fused, knn_points_per_cell, tc_timeline)", key);
   return B200_E_INVALID;
 }
 
@@ -90,6 +96,7 @@ int64_t b200_get_option(const char* key) {
   if (key && strcmp(key, "knn_points_per_cell") == 0) return b200::get_grid_points_per_cell();
   if (key && strcmp(key, "tensor_core_paths") == 0) return b200::g_tc_paths.load(std::memory_order_relaxed);
   if (key && strcmp(key, "tma_rows") == 0) return b200::g_tma_rows.load(std::memory_order_relaxed);
+  if (key && strcmp(key, "bn_backward_fused") == 0) return b200::g_bn_fused.load(std::memory_order_relaxed);
   if (key && strcmp(key, "tc_timeline") == 0)
     return static_cast<int64_t>(reinterpret_cast<intptr_t>(b200::g_tc_timeline.load(std::memory_order_relaxed)));
   return -1;

@@ -576,12 +576,10 @@ class _BNAct(torch.autograd.Function):
         lib = _lib.load()
         n, c = y1.shape
         dev = y1.device
-        red = _zeros_scratch(4 * c if y2 is not None else 2 * c, torch.float64, dev)  # consumed inside this call
+        nred = 4 * c if y2 is not None else 2 * c
+        red = _zeros_scratch(nred + 1, torch.float64, dev)  # consumed inside this call; +1: the grid-barrier counter
         red1 = red[:2 * c]
-        red2 = red[2 * c:] if y2 is not None else None
-        _call("b200_affine_act_bwd_reduce", _p(grad_out), _p(out), ctx.slope, _p(y1), _p(aff1[2]), _p(aff1[3]), _p(red1),
-                                            _p(y2), _p(aff2[2]) if y2 is not None else None,
-                                            _p(aff2[3]) if y2 is not None else None, _p(red2), n, c, _stream())
+        red2 = red[2 * c:4 * c] if y2 is not None else None
         gy1 = torch.empty_like(y1)
         gy2 = torch.empty_like(y2) if y2 is not None else None
         tr = ctx.training
@@ -597,11 +595,20 @@ class _BNAct(torch.autograd.Function):
                 if pg2 is None or pb2 is None:
                     tmp = torch.zeros(2 * c, dtype=torch.float32, device=dev)
                     pg2, pb2 = gg2, gb2 = tmp[:c], tmp[c:]
+            # reduce + apply in one call (one launch with a grid barrier for the small levels, else the two kernels)
+            _call("b200_affine_act_bwd", _p(grad_out), _p(out), ctx.slope,
+                  _p(y1), _p(g1), _p(aff1[2]), _p(aff1[3]), _p(red1), _p(gy1), _p(pg1), _p(pb1),
+                  _p(y2), _p(g2), _p(aff2[2]) if y2 is not None else None, _p(aff2[3]) if y2 is not None else None,
+                  _p(red2), _p(gy2), _p(pg2), _p(pb2), _p(red[nred:]), n, c, _stream())
+            return (gy1, None, gg1, gb1, None, None, None, gy2, None, gg2, gb2, None, None, None, None, None, None)
+        _call("b200_affine_act_bwd_reduce", _p(grad_out), _p(out), ctx.slope, _p(y1), _p(aff1[2]), _p(aff1[3]), _p(red1),
+                                            _p(y2), _p(aff2[2]) if y2 is not None else None,
+                                            _p(aff2[3]) if y2 is not None else None, _p(red2), n, c, _stream())
         _call("b200_affine_act_bwd_apply",
             _p(grad_out), _p(out), ctx.slope,
-            _p(y1), _p(g1), _p(aff1[2]), _p(aff1[3]), _p(red1) if tr else None, _p(aff1[0]), _p(gy1), _p(pg1), _p(pb1),
+            _p(y1), _p(g1), _p(aff1[2]), _p(aff1[3]), None, _p(aff1[0]), _p(gy1), None, None,
             _p(y2), _p(g2), _p(aff2[2]) if y2 is not None else None, _p(aff2[3]) if y2 is not None else None,
-            _p(red2) if (tr and y2 is not None) else None, _p(aff2[0]) if y2 is not None else None, _p(gy2), _p(pg2), _p(pb2),
+            None, _p(aff2[0]) if y2 is not None else None, _p(gy2), None, None,
             n, c, _stream())
         if not tr:  # eval-mode statistics: the same sums are the affine gradients
             gg1, gb1 = red1[c:].float(), red1[:c].float()

@@ -611,6 +611,70 @@ def test_bn_act(lib, n, c, dual, training):
         assert_close(gb2.running_var, bn2.running_var, atol=1e-6, rtol=1e-5, what="running_var 2")
 
 
+@pytest.mark.parametrize("n,c", [(12800, 128), (51200, 32), (3200, 512), (800, 512), (12345, 64), (204800, 8), (4099, 20)])
+@pytest.mark.parametrize("dual", [False, True])
+def test_bn_backward_one_launch_matches_two_kernels(lib, n, c, dual):
+    """b200_affine_act_bwd can run reduce + apply of the small levels as ONE kernel with a grid barrier (n * c <= 2^21;
+    option bn_backward_fused, off by default because it measured slower):
+    against fp64 torch autograd, against the two-kernel path (option bn_backward_fused = 0) to fp32 round-off, repeated
+    calls (the barrier counter and the sums come from the zeroed scratch arena every time), and the kernel name from CUPTI."""
+    import copy
+
+    from myria3d_b200 import ops
+    from torch.profiler import ProfilerActivity, profile
+
+    g = torch.Generator().manual_seed(n + c)
+    y1 = (torch.randn(n, c, generator=g) * 2 + 0.7).to(DEV)
+    y2 = (torch.randn(n, c, generator=g) - 0.3).to(DEV)
+    go = torch.randn(n, c, generator=g).to(DEV)
+    bn1 = torch.nn.BatchNorm1d(c, eps=1e-6, momentum=0.01)
+    bn1.weight.data.uniform_(0.5, 1.5, generator=g)
+    bn1.bias.data.uniform_(-0.5, 0.5, generator=g)
+    bn2 = copy.deepcopy(bn1)
+    bn1, bn2 = bn1.to(DEV).train(), bn2.to(DEV).train()
+
+    def stats(t):
+        td = t.detach().double()
+        return torch.cat([td.sum(0), (td * td).sum(0)])[None, :].contiguous()
+
+    def run():
+        m1, m2 = copy.deepcopy(bn1), copy.deepcopy(bn2)
+        d1, d2 = y1.clone().requires_grad_(True), y2.clone().requires_grad_(True)
+        out = ops.bn_act(d1, stats(d1), m1, 0.2, y2=d2 if dual else None, stats2=stats(d2) if dual else None, bn2=m2 if dual else None)
+        out.backward(go)
+        torch.cuda.synchronize()
+        return d1.grad, (d2.grad if dual else None), m1.weight.grad, m1.bias.grad
+
+    before = int(lib.b200_get_option(b"bn_backward_fused"))
+    try:
+        lib.b200_set_option(b"bn_backward_fused", 1)
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            a = run()
+        a2 = run()
+        lib.b200_set_option(b"bn_backward_fused", 0)
+        b = run()
+    finally:
+        lib.b200_set_option(b"bn_backward_fused", before)
+    names = " ".join(e.key for e in prof.key_averages())
+    small = n * c <= (1 << 21) and c % 4 == 0
+    assert ("affine_act_bwd_fused_kernel" in names) == small, names
+    # fp64 reference through torch autograd
+    r1, r2 = y1.double().clone().requires_grad_(True), y2.double().clone().requires_grad_(True)
+    q1, q2 = copy.deepcopy(bn1).double(), copy.deepcopy(bn2).double()
+    pre = q1(r1) + (q2(r2) if dual else 0)
+    F.leaky_relu(pre, 0.2).backward(go.double())
+    assert rel_err(a[0], r1.grad) < 2e-5, rel_err(a[0], r1.grad)
+    assert rel_err(a[2], q1.weight.grad) < 1e-5 and rel_err(a[3], q1.bias.grad) < 1e-5
+    if dual:
+        assert rel_err(a[1], r2.grad) < 2e-5
+    for x, y in zip(a, b):  # one launch == two launches (fp64 atomics in a different order: round-off of the fp32 results)
+        if x is not None:
+            assert rel_err(x, y.double()) < 1e-6, rel_err(x, y.double())
+    for x, y in zip(a, a2):
+        if x is not None:
+            assert rel_err(x, y.double()) < 1e-6
+
+
 def test_bn_single_row_raises(lib):
     from myria3d_b200 import ops
 
