@@ -282,3 +282,25 @@ def test_checkpoint_unpickler_does_not_resolve_code_globals(tmp_path):
     ck = load_lightning_checkpoint(str(path))
     assert torch.equal(ck["state_dict"]["model.fc0.weight"], torch.ones(2, 3)) and ck["epoch"] == 1
     assert not (tmp_path / "pwned").exists()
+
+
+def test_b200_options_env_is_applied_by_the_binding():
+    """``B200_OPTIONS=key=value,...`` is read by the PYTHON binding and applied through the public b200_set_option (the
+    library itself reads no environment); defaults: TMA row kernels on (7), one-launch BatchNorm backward off; an unknown
+    key fails loudly at load time."""
+    import subprocess
+    import sys
+
+    code = ("from myria3d_b200 import _lib; l = _lib.load(); "
+            "print(l.b200_get_option(b'tma_rows'), l.b200_get_option(b'bn_backward_fused'), l.b200_get_option(b'tensor_core_paths'))")
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    env.pop("B200_OPTIONS", None)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd=ROOT)
+    assert out.returncode == 0, out.stderr
+    assert out.stdout.split() == ["7", "0", "31"]
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT,
+                         env=dict(env, B200_OPTIONS="tma_rows=3, bn_backward_fused=1"))
+    assert out.returncode == 0, out.stderr
+    assert out.stdout.split() == ["3", "1", "31"]
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT, env=dict(env, B200_OPTIONS="no_such_option=1"))
+    assert out.returncode != 0 and "unknown option" in out.stderr
