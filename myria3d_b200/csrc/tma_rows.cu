@@ -107,6 +107,17 @@ tma_rows_nn_kernel(const __grid_constant__ CUtensorMap map0, const __grid_consta
   const int tid = threadIdx.x;
   const int cg = tid % C::NCG, rg = tid / C::NCG;
 
+  // The weights are fetched FIRST, all loads of a thread in flight at once (ncu, round 2: a load -> store loop here made
+  // four dependent L2 round trips and held 20 % of the kernel's stall samples), and parked in registers while the
+  // barriers are set up and the first tiles are requested.
+  constexpr int NWREG = C::KP * MP / TR_THREADS;
+  static_assert(C::KP * MP % TR_THREADS == 0, "weight staging");
+  float wreg[NWREG];
+#pragma unroll
+  for (int i = 0; i < NWREG; ++i) {
+    const int t = tid + i * TR_THREADS;  // global reads coalesced in both orientations
+    wreg[i] = w_out_major ? __ldg(w + (int64_t)(t / C::KP) * w_ld + (t % C::KP)) : __ldg(w + (int64_t)(t / MP) * w_ld + (t % MP));
+  }
   if (tid == 0) {
     for (int s = 0; s < C::STAGES; ++s) mbar_init(&full[s], 1);
     mbar_fence_init();
@@ -125,17 +136,12 @@ tma_rows_nn_kernel(const __grid_constant__ CUtensorMap map0, const __grid_consta
     tma_load_2d(dst, pm0, 0, row0, bar);
     if constexpr (NSUB == 2) tma_load_2d(dst + C::SUB_BYTES, pm1, col1, row0, bar);
   };
-  // the first tiles are on their way while the weights are staged (ncu, round 2: the two latencies in sequence were a
-  // fifth of the kernel)
   if (tid == 0)
     for (int i = 0; i < C::STAGES && i < my_tiles; ++i) issue(i);
-  for (int t = tid; t < C::KP * MP; t += TR_THREADS) {  // Bs[k][m]; global reads coalesced in both orientations
-    if (w_out_major) {
-      const int m = t / C::KP, k = t % C::KP;
-      Bs[k * MP + m] = __ldg(w + (int64_t)m * w_ld + k);
-    } else {
-      Bs[t] = __ldg(w + (int64_t)(t / MP) * w_ld + (t % MP));
-    }
+#pragma unroll
+  for (int i = 0; i < NWREG; ++i) {  // Bs[k][m]
+    const int t = tid + i * TR_THREADS;
+    Bs[w_out_major ? (t % C::KP) * MP + (t / C::KP) : t] = wreg[i];
   }
   __syncthreads();
 
