@@ -36,6 +36,12 @@ def test_library_rejects_bad_arguments_without_gpu(lib):
         _lib.check(rc, "b200_knn")
     rc = lib.b200_lfa_fwd(None, None, None, None, None, None, None, 10, 16, 16, None)
     assert rc == 1
+    # train-mode BatchNorm backward in one call: statistics, `red` and the output gradient are required
+    rc = lib.b200_affine_act_bwd(None, None, 0.2, None, None, None, None, None, None, None, None, None, None, None, None, None,
+                                 None, None, None, None, 100, 32, None)
+    assert rc == 1 and b"b200_affine_act_bwd" in lib.b200_last_error()
+    assert lib.b200_set_option(b"no_such_option", 1) == 1 and b"unknown option" in lib.b200_last_error()
+    assert lib.b200_get_option(b"no_such_option") == -1
 
 
 def test_no_cpu_fallback():
